@@ -1,0 +1,54 @@
+/*
+ * qnnpack_cuda.h — additive, non-breaking extensions of the qnnpack.h C ABI for CUDA callers.
+ * Nothing here exists in the reference; a caller that only knows qnnpack.h never needs it.
+ * Plain C types only (streams are passed as void* == cudaStream_t) so that cgo / JNI / ctypes
+ * bindings do not need the CUDA headers.
+ */
+#pragma once
+
+#include "qnnpack.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Stream every later qnnp_run_operator / qnnp_cuda_run_operator_async enqueues on.
+ * NULL restores the library's own non-blocking stream.  Not thread-safe against concurrent runs. */
+enum qnnp_status qnnp_cuda_set_stream(void* cuda_stream);
+void* qnnp_cuda_get_stream(void);
+
+/* Device ordinal selected by qnnp_initialize(), or -1 before initialisation. */
+int qnnp_cuda_get_device(void);
+
+/* Like qnnp_run_operator (reference include/qnnpack.h:327-329, src/operator-run.c:639) but only enqueues:
+ * valid only for operators whose input and output given to qnnp_setup_* are DEVICE pointers
+ * (host pointers need the synchronous call, which stages the copies); returns
+ * qnnp_status_invalid_parameter otherwise.  Completion is observed through the stream. */
+enum qnnp_status qnnp_cuda_run_operator_async(qnnp_operator_t op);
+
+/* Packed-weight blob of a convolution / fully-connected operator, resident on the device.
+ * Multi-GPU data parallelism replicates weights by broadcasting this blob (e.g. ncclBroadcast /
+ * torch.distributed.broadcast over NVLink) into the identically-created operator on every rank;
+ * the steady-state run has no collective.  Returns qnnp_status_invalid_parameter for NULL. */
+enum qnnp_status qnnp_cuda_operator_packed_weights(qnnp_operator_t op, void** device_ptr, size_t* size_bytes);
+
+/* Number of kernels the library has launched since qnnp_initialize() (bench.py's gpu_launches). */
+unsigned long long qnnp_cuda_launch_count(void);
+
+/* Stand-alone Q31 requantization int32 -> uint8 on the device (the epilogue as its own kernel);
+ * the counterpart of the reference's qnnp_requantize_q31__scalar
+ * (src/qnnpack/requantization-stubs.h:22-29, src/requantization/q31-scalar.c:17).
+ * `input`/`output` may be host or device pointers; synchronous. scale must be in [2^-32, 1). */
+enum qnnp_status qnnp_cuda_requantize_q31(
+    size_t n, const int32_t* input, float scale, uint8_t zero_point, uint8_t qmin, uint8_t qmax, uint8_t* output);
+
+/* Debug aid for kernel bring-up: when non-NULL, the next runs of tensor-core operators also dump
+ * their raw int32 accumulators ([work item][128][n_mma]) to this DEVICE buffer. */
+void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer);
+
+/* Name of the kernel family an operator was routed to: "igemm-gemm", "igemm-conv", "dwconv3x3", "direct". */
+const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op);
+
+#ifdef __cplusplus
+}
+#endif

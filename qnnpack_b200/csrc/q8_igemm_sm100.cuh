@@ -1,0 +1,55 @@
+// Parameters shared by the host launcher and the tcgen05 implicit-GEMM kernel (q8gemm + q8conv).
+#pragma once
+#include <stdint.h>
+
+#include "requant_math.h"
+
+namespace q8 {
+
+constexpr int kTileM = 128;            // rows (output pixels) per work item = UMMA M
+constexpr int kChunkBytes = kTileM * 16;  // one 16-byte K-chunk of an A tile: [128 rows][16 B]
+constexpr int kMaxStages = 16;
+constexpr int kMaxNMma = 256;          // UMMA N limit; also the TMEM column stride of an accumulator stage
+constexpr int kOnesCols = 16;          // extra B rows: row 0 of the block is all-ones -> per-row sum of A
+constexpr int kMaxNTile = kMaxNMma - kOnesCols;
+
+enum IgemmMode : int { kModeGemm = 0, kModeConv = 1 };
+
+struct IgemmParams {
+  const uint8_t* in;
+  uint8_t* out;
+  const uint8_t* wpack;  // [group][n_tile] blocks, each [nkc][n_mma][16 B]  (K-major, no-swizzle core matrices)
+  const int32_t* bias;   // [group][n_tiles * n_tile] folded bias (reference pack.h:24,43,63,84)
+  int32_t* dbg_acc;      // optional: raw accumulators [item][128][n_mma]
+
+  long long M;           // rows per group = batch * out_h * out_w
+  long long m_tiles;
+  long long total_items; // groups * m_tiles * n_tiles
+  long long in_stride, out_stride;
+  int groups, gic, goc;
+
+  // conv geometry (kModeConv)
+  int in_h, in_w, out_h, out_w, kh, kw, stride_h, stride_w, dil_h, dil_w, pad_top, pad_left;
+
+  // tiling
+  int K;          // kh*kw*gic
+  int nkc;        // 16-byte K chunks incl. padding, even
+  int nkc_real;   // ceil(K/16)
+  int skc;        // chunks per pipeline stage, even
+  int k_stages;   // ceil(nkc / skc)
+  int n_tiles, n_tile, n_mma;
+  int b_resident; // 1: all packed weights live in smem for the whole kernel
+  int num_stages; // A(+B) ring depth
+  int stage_bytes;
+  int out_mode;   // 0: per-row stores from registers; 1: whole-tile bulk store via smem staging
+  int out_vec;    // direct stores: widest power-of-two (<=16) dividing base address, out_stride and column offsets
+  int rq_mode;    // 0: fused, shift>=1, no clamp needed; 1: fused, shift>=1, clamp; 2: shift==0; 3: exact slow form
+
+  // smem carve-up (byte offsets into dynamic smem, 1024-aligned base)
+  int smem_b_off, smem_a_off, smem_stage_off, smem_total;
+
+  int izp, kzp;
+  Q8Requant rq;
+};
+
+}  // namespace q8

@@ -1,0 +1,743 @@
+// Host side of libqnnpack.so: the qnnpack.h C ABI implemented over the sm_100a kernels.
+//
+// Mirrors, entry point by entry point (reference paths relative to its root):
+//   qnnp_initialize / qnnp_deinitialize          src/init.c:244-270
+//   qnnp_create_convolution2d_nhwc_q8            src/convolution.c:39-378   (validation order, kernel choice :180-189)
+//   qnnp_setup_convolution2d_nhwc_q8             src/convolution.c:380-492
+//   qnnp_create/setup_fully_connected_nc_q8      src/fully-connected.c:25-161
+//   qnnp_run_operator                            src/operator-run.c:639-844 (dwconv / gemm / conv cases)
+//   qnnp_delete_operator                         src/operator-delete.c:15-28
+// What changes: weights are packed for UMMA instead of for 4x4c2 SSE2 tiles (src/qnnpack/pack.h), no
+// indirection buffer is ever built (src/indirection.c), run = one kernel launch on a CUDA stream.
+// There is no CPU fallback: without a compute-capability-10.x device initialisation fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "../../include/qnnpack.h"
+#include "../../include/qnnpack_cuda.h"
+#include "q8_dwconv_sm100.cuh"
+#include "q8_igemm_sm100.cuh"
+
+namespace q8 {
+cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, int grid, cudaStream_t stream);
+}
+
+#define QNNP_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// library state
+// ------------------------------------------------------------------------------------------------
+struct Library {
+  bool initialized = false;
+  enum qnnp_status init_status = qnnp_status_uninitialized;
+  int device = -1;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::atomic<unsigned long long> launches{0};
+  int32_t* dbg_acc = nullptr;
+};
+Library g_lib;
+pthread_once_t g_once = PTHREAD_ONCE_INIT;
+
+void log_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "Error in QNNPACK(b200): ");
+  vfprintf(stderr, fmt, ap);
+  fputc('\n', stderr);
+  va_end(ap);
+}
+
+enum qnnp_status map_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return qnnp_status_success;
+  log_error("%s: %s", what, cudaGetErrorString(e));
+  return e == cudaErrorMemoryAllocation ? qnnp_status_out_of_memory : qnnp_status_unsupported_hardware;
+}
+
+void init_once() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    log_error("no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+    g_lib.init_status = qnnp_status_unsupported_hardware;
+    return;
+  }
+  int dev = 0;
+  const char* env = getenv("QNNP_CUDA_DEVICE");
+  if (env != nullptr) {
+    dev = atoi(env);
+  } else if (cudaGetDevice(&dev) != cudaSuccess) {
+    dev = 0;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+    log_error("device %d is not a compute-capability 10.x (B200-class) GPU", dev);
+    g_lib.init_status = qnnp_status_unsupported_hardware;
+    return;
+  }
+  if (cudaSetDevice(dev) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g_lib.own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_lib.init_status = qnnp_status_unsupported_hardware;
+    return;
+  }
+  g_lib.device = dev;
+  g_lib.num_sms = prop.multiProcessorCount;
+  g_lib.max_smem_optin = (int) prop.sharedMemPerBlockOptin;
+  g_lib.stream = g_lib.own_stream;
+  g_lib.initialized = true;
+  g_lib.init_status = qnnp_status_success;
+}
+
+bool is_device_pointer(const void* ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
+inline size_t ceil_div(size_t x, size_t q) { return (x + q - 1) / q; }
+
+int pow2_align(uintptr_t v, int cap) {  // largest power of two <= cap dividing v (v == 0 -> cap)
+  int a = cap;
+  while (a > 1 && (v % (uintptr_t) a) != 0) a >>= 1;
+  return a;
+}
+
+enum KernelKind { kKindNone = 0, kKindIgemmGemm, kKindIgemmConv, kKindDw3x3, kKindDirect };
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// operator object (opaque to users; reference src/qnnpack/operator.h:39-102)
+// ------------------------------------------------------------------------------------------------
+struct qnnp_operator {
+  KernelKind kind = kKindNone;
+  bool is_fc = false;
+
+  // create-time
+  uint32_t pad_top = 0, pad_right = 0, pad_bottom = 0, pad_left = 0;
+  uint32_t kh = 1, kw = 1, stride_h = 1, stride_w = 1, dil_h = 1, dil_w = 1;
+  uint32_t groups = 1;
+  size_t gic = 0, goc = 0;
+  uint8_t izp = 0, kzp = 0;
+  Q8Requant rq{};
+  int rq_mode = 3;
+
+  // device-resident packed parameters
+  void* d_weights = nullptr;   // igemm: UMMA blob; dw: int32 [9][c_pad]; direct: original kernel bytes
+  size_t weights_bytes = 0;
+  int32_t* d_bias = nullptr;   // folded bias
+  size_t bias_count = 0;
+
+  // igemm tiling
+  int K = 0, nkc = 0, nkc_real = 0, skc = 0, k_stages = 0, n_tiles = 0, n_tile = 0, n_mma = 0;
+  int b_resident = 0, num_stages = 0, stage_bytes = 0;
+  int smem_b_off = 0, smem_a_off = 0, smem_stage_off = 0, smem_total = 0;
+  bool bulk_capable = false;
+  int c_pad = 0;  // dw
+
+  // setup-time
+  size_t batch = 0, in_h = 0, in_w = 0, out_h = 0, out_w = 0;
+  const uint8_t* input = nullptr;
+  uint8_t* output = nullptr;
+  size_t in_stride = 0, out_stride = 0;
+  bool in_on_device = false, out_on_device = false;
+  // staging for host pointers
+  uint8_t* d_in = nullptr;
+  uint8_t* d_out = nullptr;
+  size_t d_in_cap = 0, d_out_cap = 0;
+};
+
+namespace {
+
+void free_operator(qnnp_operator* op) {
+  if (op == nullptr) return;
+  cudaFree(op->d_weights);
+  cudaFree(op->d_bias);
+  cudaFree(op->d_in);
+  cudaFree(op->d_out);
+  delete op;
+}
+
+int select_rq_mode(const Q8Requant& rq) {
+  if (!rq.fused) return 3;
+  if (rq.shift == 0) return 2;
+  return (rq.qmin == 0 && rq.qmax == 255) ? 0 : 1;
+}
+
+bool scale_ok(float s) { return s > 0.0f && isnormal(s); }
+
+uint32_t f32_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, sizeof u);
+  return u;
+}
+
+// Folded bias: b + K*izp*kzp - izp*sum_k w   (src/qnnpack/pack.h:24,29,43 / :63,84 / :146,159), int32 wrap-around.
+int32_t fold_bias(int32_t b, size_t k_total, uint8_t izp, uint8_t kzp, const uint8_t* w) {
+  uint32_t wsum = 0;
+  for (size_t i = 0; i < k_total; i++) wsum += w[i];
+  return (int32_t) ((uint32_t) b + (uint32_t) k_total * (uint32_t) izp * (uint32_t) kzp - wsum * (uint32_t) izp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// igemm planning + packing
+// ------------------------------------------------------------------------------------------------
+constexpr int kCtlReserve = 2048;  // static SmemCtl + 1024-byte alignment slack
+
+enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
+  const size_t ks = (size_t) op->kh * op->kw;
+  const size_t K = ks * op->gic;
+  if (K > (size_t) 1 << 24 || op->goc > (size_t) 1 << 24) {
+    log_error("convolution too large for the tensor-core path (K=%zu, N=%zu)", K, op->goc);
+    return qnnp_status_unsupported_parameter;
+  }
+  op->K = (int) K;
+  op->nkc_real = (int) ceil_div(K, 16);
+  op->nkc = (int) round_up(op->nkc_real, 2);
+  const int n_pad = (int) round_up(op->goc, 16);
+  if (n_pad <= q8::kMaxNTile) {
+    op->n_tiles = 1;
+    op->n_tile = n_pad;
+  } else {
+    op->n_tiles = (int) ceil_div(n_pad, q8::kMaxNTile);
+    op->n_tile = (int) round_up(ceil_div(n_pad, op->n_tiles), 16);
+  }
+  op->n_mma = op->n_tile + q8::kOnesCols;
+  op->skc = op->nkc < 8 ? op->nkc : 8;
+  op->k_stages = (int) ceil_div(op->nkc, op->skc);
+
+  const int smem_max = g_lib.max_smem_optin - kCtlReserve;
+  op->bulk_capable = op->groups == 1 && op->n_tiles == 1 && (op->goc % 4) == 0;
+  const int staging = op->bulk_capable ? 2 * q8::kTileM * (int) op->goc : 0;
+  const size_t w_total = (size_t) op->groups * op->n_tiles * op->nkc * op->n_mma * 16;
+  const int a_stage = op->skc * q8::kChunkBytes;
+  op->b_resident = (w_total + (size_t) staging + 3u * (size_t) a_stage <= (size_t) smem_max) ? 1 : 0;
+  op->stage_bytes = a_stage + (op->b_resident ? 0 : op->skc * op->n_mma * 16);
+  const int b_bytes = op->b_resident ? (int) w_total : 0;
+  int stages = (smem_max - b_bytes - staging) / op->stage_bytes;
+  if (stages > q8::kMaxStages) stages = q8::kMaxStages;
+  if (stages < 2) {
+    log_error("shared-memory plan failed (stage %d B, staging %d B)", op->stage_bytes, staging);
+    return qnnp_status_unsupported_parameter;
+  }
+  op->num_stages = stages;
+  op->smem_b_off = 0;
+  op->smem_a_off = (int) round_up(b_bytes, 128);
+  op->smem_stage_off = op->smem_a_off + stages * op->stage_bytes;
+  op->smem_total = op->smem_stage_off + staging + 1024;
+
+  // ---- pack: [group][n_tile][k-chunk][row][16 B]; row n_tile of every block is the all-ones row ----
+  std::vector<uint8_t> blob(w_total, 0);
+  const size_t bias_count = (size_t) op->groups * op->n_tiles * op->n_tile;
+  std::vector<int32_t> fbias(bias_count, 0);
+  for (uint32_t g = 0; g < op->groups; g++) {
+    for (int nt = 0; nt < op->n_tiles; nt++) {
+      uint8_t* blk = blob.data() + ((size_t) g * op->n_tiles + nt) * op->nkc * op->n_mma * 16;
+      for (int r = 0; r < op->n_tile; r++) {
+        const size_t oc = (size_t) nt * op->n_tile + r;
+        if (oc >= op->goc) break;
+        const uint8_t* wrow = kernel + ((size_t) g * op->goc + oc) * K;
+        for (size_t k = 0; k < K; k++) blk[((k >> 4) * op->n_mma + r) * 16 + (k & 15)] = wrow[k];
+        fbias[((size_t) g * op->n_tiles + nt) * op->n_tile + r] = fold_bias(bias[g * op->goc + oc], K, op->izp, op->kzp, wrow);
+      }
+      for (size_t k = 0; k < K; k++) blk[((k >> 4) * op->n_mma + op->n_tile) * 16 + (k & 15)] = 1;
+    }
+  }
+  op->weights_bytes = w_total;
+  op->bias_count = bias_count;
+  cudaError_t e = cudaMalloc(&op->d_weights, w_total);
+  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, bias_count * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, blob.data(), w_total, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), bias_count * sizeof(int32_t), cudaMemcpyHostToDevice);
+  return map_cuda(e, "uploading packed weights");
+}
+
+enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
+  const size_t C = op->groups;
+  op->c_pad = (int) round_up(C, 4);
+  std::vector<int32_t> w32((size_t) 9 * op->c_pad, 0), fbias(op->c_pad, 0);
+  for (size_t c = 0; c < C; c++) {
+    for (int t = 0; t < 9; t++) w32[(size_t) t * op->c_pad + c] = (int32_t) kernel[c * 9 + t] - (int32_t) op->kzp;
+    fbias[c] = fold_bias(bias[c], 9, op->izp, op->kzp, kernel + c * 9);
+  }
+  op->weights_bytes = w32.size() * sizeof(int32_t);
+  op->bias_count = fbias.size();
+  cudaError_t e = cudaMalloc(&op->d_weights, op->weights_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, fbias.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, w32.data(), op->weights_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), fbias.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  return map_cuda(e, "uploading depthwise weights");
+}
+
+enum qnnp_status pack_direct(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
+  const size_t K = (size_t) op->kh * op->kw * op->gic;
+  const size_t oc_all = (size_t) op->groups * op->goc;
+  std::vector<int32_t> fbias(oc_all);
+  for (size_t oc = 0; oc < oc_all; oc++) fbias[oc] = fold_bias(bias[oc], K, op->izp, op->kzp, kernel + oc * K);
+  op->weights_bytes = oc_all * K;
+  op->bias_count = oc_all;
+  cudaError_t e = cudaMalloc(&op->d_weights, op->weights_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, oc_all * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, kernel, op->weights_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), oc_all * sizeof(int32_t), cudaMemcpyHostToDevice);
+  return map_cuda(e, "uploading weights");
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cudaStream_t stream) {
+  const size_t M = op->batch * op->out_h * op->out_w;
+  cudaError_t e = cudaSuccess;
+  switch (op->kind) {
+    case kKindIgemmGemm:
+    case kKindIgemmConv: {
+      q8::IgemmParams p{};
+      p.in = in;
+      p.out = out;
+      p.wpack = (const uint8_t*) op->d_weights;
+      p.bias = op->d_bias;
+      p.dbg_acc = g_lib.dbg_acc;
+      p.M = (long long) M;
+      p.m_tiles = (long long) ceil_div(M, q8::kTileM);
+      p.total_items = (long long) op->groups * p.m_tiles * op->n_tiles;
+      p.in_stride = (long long) op->in_stride;
+      p.out_stride = (long long) op->out_stride;
+      p.groups = (int) op->groups, p.gic = (int) op->gic, p.goc = (int) op->goc;
+      p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
+      p.kh = (int) op->kh, p.kw = (int) op->kw, p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w;
+      p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w, p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
+      p.K = op->K, p.nkc = op->nkc, p.nkc_real = op->nkc_real, p.skc = op->skc, p.k_stages = op->k_stages;
+      p.n_tiles = op->n_tiles, p.n_tile = op->n_tile, p.n_mma = op->n_mma;
+      p.b_resident = op->b_resident, p.num_stages = op->num_stages, p.stage_bytes = op->stage_bytes;
+      p.smem_b_off = op->smem_b_off, p.smem_a_off = op->smem_a_off, p.smem_stage_off = op->smem_stage_off;
+      p.smem_total = op->smem_total;
+      p.izp = op->izp, p.kzp = op->kzp;
+      p.rq = op->rq;
+      p.rq_mode = op->rq_mode;
+      // output path
+      const bool bulk = op->bulk_capable && op->out_stride == op->goc && ((uintptr_t) out % 16) == 0 &&
+          getenv("QNNP_CUDA_NO_BULK_STORE") == nullptr;
+      p.out_mode = bulk ? 1 : 0;
+      int ov = pow2_align((uintptr_t) out, 16);
+      ov = pow2_align((uintptr_t) op->out_stride, ov);
+      if (op->groups > 1) ov = pow2_align((uintptr_t) op->goc, ov);  // group offset g*goc (tile offsets are multiples of 16)
+      p.out_vec = ov;
+      // loader vector width
+      int vec = pow2_align((uintptr_t) in, 16);
+      vec = pow2_align((uintptr_t) op->in_stride, vec);
+      vec = pow2_align((uintptr_t) op->gic, vec);
+      if (vec < 4) vec = 1;
+      const int mode = op->kind == kKindIgemmGemm ? q8::kModeGemm : q8::kModeConv;
+      long long grid = p.total_items < g_lib.num_sms ? p.total_items : g_lib.num_sms;
+      e = q8::launch_q8_igemm(p, mode, vec, (int) grid, stream);
+      break;
+    }
+    case kKindDw3x3: {
+      q8::DwParams p{};
+      p.in = in, p.out = out;
+      p.w32 = (const int32_t*) op->d_weights;
+      p.bias = op->d_bias;
+      p.in_stride = (long long) op->in_stride, p.out_stride = (long long) op->out_stride;
+      p.batch = (int) op->batch, p.channels = (int) op->groups, p.c_pad = op->c_pad;
+      p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
+      p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w, p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w;
+      p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
+      p.izp = op->izp;
+      p.rq = op->rq, p.rq_mode = op->rq_mode;
+      int cv = pow2_align((uintptr_t) in, 4);
+      cv = pow2_align((uintptr_t) out, cv);
+      cv = pow2_align((uintptr_t) op->in_stride, cv);
+      cv = pow2_align((uintptr_t) op->out_stride, cv);
+      cv = pow2_align((uintptr_t) op->groups, cv);
+      e = q8::launch_q8_dwconv3x3(p, cv == 4 ? 4 : 1, stream);
+      break;
+    }
+    case kKindDirect: {
+      q8::DirectParams p{};
+      p.in = in, p.out = out;
+      p.w = (const uint8_t*) op->d_weights;
+      p.bias = op->d_bias;
+      p.in_stride = (long long) op->in_stride, p.out_stride = (long long) op->out_stride;
+      p.total = (long long) M * op->groups * op->goc;
+      p.groups = (int) op->groups, p.gic = (int) op->gic, p.goc = (int) op->goc;
+      p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
+      p.kh = (int) op->kh, p.kw = (int) op->kw;
+      p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w, p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w;
+      p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
+      p.izp = op->izp, p.kzp = op->kzp;
+      p.rq = op->rq;
+      e = q8::launch_q8_direct_conv(p, stream);
+      break;
+    }
+    default:
+      return qnnp_status_invalid_parameter;
+  }
+  g_lib.launches.fetch_add(1);
+  return map_cuda(e, "kernel launch");
+}
+
+enum qnnp_status ensure_capacity(uint8_t** buf, size_t* cap, size_t need) {
+  if (*cap >= need) return qnnp_status_success;
+  cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc((void**) buf, need);
+  if (e != cudaSuccess) return map_cuda(e, "allocating device staging buffer");
+  *cap = need;
+  return qnnp_status_success;
+}
+
+enum qnnp_status run_impl(qnnp_operator* op, bool async) {
+  if (op == nullptr) return qnnp_status_invalid_parameter;
+  if (op->batch == 0) return qnnp_status_success;  // src/operator-run.c:642
+  cudaStream_t stream = g_lib.stream;
+  if (op->in_on_device && op->out_on_device) {
+    enum qnnp_status st = launch(op, op->input, op->output, stream);
+    if (st != qnnp_status_success || async) return st;
+    return map_cuda(cudaStreamSynchronize(stream), "stream synchronize");
+  }
+  if (async) return qnnp_status_invalid_parameter;
+
+  // host pointers: stage through device buffers inside the (synchronous) call
+  const size_t pixels_in = op->batch * op->in_h * op->in_w, pixels_out = op->batch * op->out_h * op->out_w;
+  const size_t in_bytes = (pixels_in - 1) * op->in_stride + op->groups * op->gic;
+  const size_t out_bytes = (pixels_out - 1) * op->out_stride + op->groups * op->goc;
+  const uint8_t* din = op->input;
+  uint8_t* dout = op->output;
+  enum qnnp_status st;
+  if (!op->in_on_device) {
+    if ((st = ensure_capacity(&op->d_in, &op->d_in_cap, in_bytes)) != qnnp_status_success) return st;
+    if ((st = map_cuda(cudaMemcpyAsync(op->d_in, op->input, in_bytes, cudaMemcpyHostToDevice, stream), "H2D input")) !=
+        qnnp_status_success)
+      return st;
+    din = op->d_in;
+  }
+  if (!op->out_on_device) {
+    if ((st = ensure_capacity(&op->d_out, &op->d_out_cap, out_bytes)) != qnnp_status_success) return st;
+    dout = op->d_out;
+    if (op->out_stride != op->groups * op->goc) {
+      // bytes between pixels must survive untouched, as in the reference (ukernels store exactly N bytes)
+      if ((st = map_cuda(cudaMemcpyAsync(op->d_out, op->output, out_bytes, cudaMemcpyHostToDevice, stream),
+                         "H2D output gaps")) != qnnp_status_success)
+        return st;
+    }
+  }
+  if ((st = launch(op, din, dout, stream)) != qnnp_status_success) return st;
+  if (!op->out_on_device) {
+    if ((st = map_cuda(cudaMemcpyAsync(op->output, op->d_out, out_bytes, cudaMemcpyDeviceToHost, stream), "D2H output")) !=
+        qnnp_status_success)
+      return st;
+  }
+  return map_cuda(cudaStreamSynchronize(stream), "stream synchronize");
+}
+
+size_t output_dimension(size_t padded_input, size_t kernel, size_t dilation, size_t subsampling) {
+  const size_t effective_kernel = (kernel - 1) * dilation + 1;  // src/convolution.c:29-37
+  return (padded_input - effective_kernel) / subsampling + 1;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+QNNP_EXPORT enum qnnp_status qnnp_initialize(void) {
+  pthread_once(&g_once, init_once);
+  return g_lib.init_status;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_deinitialize(void) { return qnnp_status_success; }
+
+QNNP_EXPORT enum qnnp_status qnnp_create_convolution2d_nhwc_q8(
+    uint32_t input_padding_top, uint32_t input_padding_right, uint32_t input_padding_bottom, uint32_t input_padding_left,
+    uint32_t kernel_height, uint32_t kernel_width, uint32_t subsampling_height, uint32_t subsampling_width,
+    uint32_t dilation_height, uint32_t dilation_width, uint32_t groups, size_t group_input_channels,
+    size_t group_output_channels, uint8_t input_zero_point, float input_scale, uint8_t kernel_zero_point,
+    float kernel_scale, const uint8_t* kernel, const int32_t* bias, uint8_t output_zero_point, float output_scale,
+    uint8_t output_min, uint8_t output_max, uint32_t flags, qnnp_operator_t* convolution_out) {
+  (void) flags;  // ignored by the reference as well (src/convolution.c:63)
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_convolution2d_nhwc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  // validation order: src/convolution.c:74-115
+  if (kernel_width == 0 || kernel_height == 0) {
+    log_error("failed to create convolution with %ux%u kernel: kernel dimensions must be non-zero", kernel_width, kernel_height);
+    return qnnp_status_invalid_parameter;
+  }
+  if (subsampling_width == 0 || subsampling_height == 0) {
+    log_error("failed to create convolution with %ux%u subsampling: subsampling dimensions must be non-zero",
+              subsampling_width, subsampling_height);
+    return qnnp_status_invalid_parameter;
+  }
+  if (dilation_width == 0 || dilation_height == 0) {
+    log_error("failed to create convolution with %ux%u dilation: dilation dimensions must be non-zero", dilation_width,
+              dilation_height);
+    return qnnp_status_invalid_parameter;
+  }
+  if (!scale_ok(input_scale) || !scale_ok(kernel_scale) || !scale_ok(output_scale)) {
+    log_error("failed to create convolution with %.7g input, %.7g kernel, %.7g output scale: scales must be finite and positive",
+              input_scale, kernel_scale, output_scale);
+    return qnnp_status_invalid_parameter;
+  }
+  // fp32, in this order: src/convolution.c:161
+  const float convolution_scale = input_scale * kernel_scale / output_scale;
+  if (convolution_scale >= 1.0f) {
+    log_error("failed to create convolution with %.7g input scale, %.7g kernel scale, and %.7g output scale: "
+              "convolution scale %.7g is greater or equal to 1.0",
+              input_scale, kernel_scale, output_scale, convolution_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  if (!(convolution_scale >= 0x1.0p-32f)) {
+    // the reference only asserts this (requantization.h:30); shifts > 31 are undefined there
+    log_error("convolution scale %.7g is below 2^-32", convolution_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  if (groups == 0 || group_input_channels == 0 || group_output_channels == 0) {
+    log_error("failed to create convolution with %u groups, %zu/%zu channels per group", groups, group_input_channels,
+              group_output_channels);
+    return qnnp_status_invalid_parameter;
+  }
+
+  qnnp_operator* op = new (std::nothrow) qnnp_operator();
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->pad_top = input_padding_top, op->pad_right = input_padding_right;
+  op->pad_bottom = input_padding_bottom, op->pad_left = input_padding_left;
+  op->kh = kernel_height, op->kw = kernel_width;
+  op->stride_h = subsampling_height, op->stride_w = subsampling_width;
+  op->dil_h = dilation_height, op->dil_w = dilation_width;
+  op->groups = groups, op->gic = group_input_channels, op->goc = group_output_channels;
+  op->izp = input_zero_point, op->kzp = kernel_zero_point;
+  op->rq = q8_make_requant(f32_bits(convolution_scale), output_zero_point, output_min, output_max);
+  op->rq_mode = select_rq_mode(op->rq);
+
+  // kernel family (reference: src/convolution.c:180-189)
+  const size_t kernel_size = (size_t) kernel_height * kernel_width;
+  const bool any_padding = (input_padding_left | input_padding_top | input_padding_right | input_padding_bottom) != 0;
+  enum qnnp_status st;
+  if (kernel_height == 3 && kernel_width == 3 && group_input_channels == 1 && group_output_channels == 1 && groups > 1) {
+    op->kind = kKindDw3x3;
+    st = pack_dw3x3(op, kernel, bias);
+  } else if (groups == 1) {
+    op->kind = (kernel_size == 1 && subsampling_height == 1 && subsampling_width == 1 && !any_padding) ? kKindIgemmGemm
+                                                                                                      : kKindIgemmConv;
+    st = plan_and_pack_igemm(op, kernel, bias);
+  } else {
+    op->kind = kKindDirect;
+    st = pack_direct(op, kernel, bias);
+  }
+  if (st != qnnp_status_success) {
+    free_operator(op);
+    return st;
+  }
+  *convolution_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_convolution2d_nhwc_q8(
+    qnnp_operator_t op, size_t batch_size, size_t input_height, size_t input_width, const uint8_t* input,
+    size_t input_stride, uint8_t* output, size_t output_stride, pthreadpool_t threadpool) {
+  (void) threadpool;
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr) return qnnp_status_invalid_parameter;
+  if (batch_size == 0) {  // src/convolution.c:396-399
+    op->batch = 0;
+    return qnnp_status_success;
+  }
+  if (input_width == 0 || input_height == 0) {
+    log_error("failed to setup convolution with %zux%zu input: input dimensions must be non-zero", input_width, input_height);
+    return qnnp_status_invalid_parameter;
+  }
+  op->batch = batch_size;
+  op->in_h = input_height, op->in_w = input_width;
+  op->input = input, op->in_stride = input_stride;
+  op->out_h = output_dimension(op->pad_top + input_height + op->pad_bottom, op->kh, op->dil_h, op->stride_h);
+  op->out_w = output_dimension(op->pad_left + input_width + op->pad_right, op->kw, op->dil_w, op->stride_w);
+  op->output = output, op->out_stride = output_stride;
+  op->in_on_device = is_device_pointer(input);
+  op->out_on_device = is_device_pointer(output);
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_create_fully_connected_nc_q8(
+    size_t input_channels, size_t output_channels, uint8_t input_zero_point, float input_scale,
+    uint8_t kernel_zero_point, float kernel_scale, const uint8_t* kernel, const int32_t* bias,
+    uint8_t output_zero_point, float output_scale, uint8_t output_min, uint8_t output_max, uint32_t flags,
+    qnnp_operator_t* fully_connected_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_fully_connected_nc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (!scale_ok(input_scale) || !scale_ok(kernel_scale) || !scale_ok(output_scale)) {  // src/fully-connected.c:49-65
+    log_error("failed to create fully connected operator with %.7g input, %.7g kernel, %.7g output scale: "
+              "scales must be finite and positive", input_scale, kernel_scale, output_scale);
+    return qnnp_status_invalid_parameter;
+  }
+  const float requantization_scale = input_scale * kernel_scale / output_scale;  // src/fully-connected.c:71
+  if (requantization_scale >= 1.0f || !(requantization_scale >= 0x1.0p-32f)) {
+    log_error("failed to create fully connected operator: requantization scale %.7g is outside [2^-32, 1)",
+              requantization_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  if (input_channels == 0 || output_channels == 0) return qnnp_status_invalid_parameter;
+  qnnp_operator* op = new (std::nothrow) qnnp_operator();
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->is_fc = true;
+  op->groups = 1, op->gic = input_channels, op->goc = output_channels;
+  op->izp = input_zero_point, op->kzp = kernel_zero_point;
+  op->rq = q8_make_requant(f32_bits(requantization_scale), output_zero_point, output_min, output_max);
+  op->rq_mode = select_rq_mode(op->rq);
+  op->kind = kKindIgemmGemm;
+  enum qnnp_status st = plan_and_pack_igemm(op, kernel, bias);
+  if (st != qnnp_status_success) {
+    free_operator(op);
+    return st;
+  }
+  *fully_connected_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_fully_connected_nc_q8(
+    qnnp_operator_t op, size_t batch_size, const uint8_t* input, size_t input_stride, uint8_t* output,
+    size_t output_stride) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr) return qnnp_status_invalid_parameter;
+  if (batch_size == 0) {
+    op->batch = 0;
+    return qnnp_status_success;
+  }
+  // src/fully-connected.c:149-158: one "image" of batch_size x 1 pixels
+  op->batch = 1;
+  op->in_h = batch_size, op->in_w = 1, op->out_h = batch_size, op->out_w = 1;
+  op->input = input, op->in_stride = input_stride;
+  op->output = output, op->out_stride = output_stride;
+  op->in_on_device = is_device_pointer(input);
+  op->out_on_device = is_device_pointer(output);
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_run_operator(qnnp_operator_t op, pthreadpool_t threadpool) {
+  (void) threadpool;
+  return run_impl(op, false);
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_delete_operator(qnnp_operator_t op) {
+  if (op == nullptr) return qnnp_status_invalid_parameter;  // src/operator-delete.c:17
+  free_operator(op);
+  return qnnp_status_success;
+}
+
+// ---- CUDA extensions (include/qnnpack_cuda.h) -----------------------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_cuda_set_stream(void* s) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  g_lib.stream = s != nullptr ? (cudaStream_t) s : g_lib.own_stream;
+  return qnnp_status_success;
+}
+QNNP_EXPORT void* qnnp_cuda_get_stream(void) { return (void*) g_lib.stream; }
+QNNP_EXPORT int qnnp_cuda_get_device(void) { return g_lib.device; }
+QNNP_EXPORT enum qnnp_status qnnp_cuda_run_operator_async(qnnp_operator_t op) { return run_impl(op, true); }
+QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_weights(qnnp_operator_t op, void** device_ptr, size_t* size_bytes) {
+  if (op == nullptr || device_ptr == nullptr || size_bytes == nullptr) return qnnp_status_invalid_parameter;
+  *device_ptr = op->d_weights;
+  *size_bytes = op->weights_bytes;
+  return qnnp_status_success;
+}
+QNNP_EXPORT unsigned long long qnnp_cuda_launch_count(void) { return g_lib.launches.load(); }
+QNNP_EXPORT void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer) { g_lib.dbg_acc = device_buffer; }
+QNNP_EXPORT const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op) {
+  if (op == nullptr) return "null";
+  switch (op->kind) {
+    case kKindIgemmGemm: return "igemm-gemm";
+    case kKindIgemmConv: return "igemm-conv";
+    case kKindDw3x3: return "dwconv3x3";
+    case kKindDirect: return "direct";
+    default: return "none";
+  }
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_cuda_requantize_q31(
+    size_t n, const int32_t* input, float scale, uint8_t zero_point, uint8_t qmin, uint8_t qmax, uint8_t* output) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (!(scale < 1.0f) || !(scale >= 0x1.0p-32f)) return qnnp_status_unsupported_parameter;
+  if (n == 0) return qnnp_status_success;
+  const Q8Requant rq = q8_make_requant(f32_bits(scale), zero_point, qmin, qmax);
+  cudaStream_t stream = g_lib.stream;
+  const bool in_dev = is_device_pointer(input), out_dev = is_device_pointer(output);
+  int32_t* din = const_cast<int32_t*>(input);
+  uint8_t* dout = output;
+  cudaError_t e = cudaSuccess;
+  if (!in_dev) {
+    e = cudaMalloc((void**) &din, n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din, input, n * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+  }
+  if (e == cudaSuccess && !out_dev) e = cudaMalloc((void**) &dout, n);
+  if (e == cudaSuccess) e = q8::launch_q8_requantize(din, dout, (long long) n, rq, stream);
+  if (e == cudaSuccess) g_lib.launches.fetch_add(1);
+  if (e == cudaSuccess && !out_dev) e = cudaMemcpyAsync(output, dout, n, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (!in_dev) cudaFree(din);
+  if (!out_dev) cudaFree(dout);
+  return map_cuda(e, "qnnp_cuda_requantize_q31");
+}
+
+// ---- operators outside the q8 hot path: link-compatible stubs ---------------------------------------
+#define QNNP_UNSUPPORTED(name, ...)                                                                   \
+  QNNP_EXPORT enum qnnp_status name(__VA_ARGS__) {                                                     \
+    if (!g_lib.initialized) return qnnp_status_uninitialized;                                          \
+    log_error(#name " is not on the q8gemm/q8conv/q8dwconv hot path and is not implemented in this library"); \
+    return qnnp_status_unsupported_parameter;                                                          \
+  }
+
+QNNP_UNSUPPORTED(qnnp_create_deconvolution2d_nhwc_q8, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                 uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, size_t, size_t, uint8_t, float, uint8_t, float,
+                 const uint8_t*, const int32_t*, uint8_t, float, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_deconvolution2d_nhwc_q8, qnnp_operator_t, size_t, size_t, size_t, const uint8_t*, size_t,
+                 uint8_t*, size_t, pthreadpool_t)
+QNNP_UNSUPPORTED(qnnp_create_global_average_pooling_nwc_q8, size_t, uint8_t, float, uint8_t, float, uint8_t, uint8_t,
+                 uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_global_average_pooling_nwc_q8, qnnp_operator_t, size_t, size_t, const uint8_t*, size_t,
+                 uint8_t*, size_t)
+QNNP_UNSUPPORTED(qnnp_create_average_pooling2d_nhwc_q8, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                 uint32_t, uint32_t, size_t, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_average_pooling2d_nhwc_q8, qnnp_operator_t, size_t, size_t, size_t, const uint8_t*, size_t,
+                 uint8_t*, size_t, pthreadpool_t)
+QNNP_UNSUPPORTED(qnnp_create_max_pooling2d_nhwc_u8, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                 uint32_t, uint32_t, uint32_t, size_t, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_max_pooling2d_nhwc_u8, qnnp_operator_t, size_t, size_t, size_t, const uint8_t*, size_t,
+                 uint8_t*, size_t, pthreadpool_t)
+QNNP_UNSUPPORTED(qnnp_create_channel_shuffle_nc_x8, size_t, size_t, uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_channel_shuffle_nc_x8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
+QNNP_UNSUPPORTED(qnnp_create_add_nc_q8, size_t, uint8_t, float, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t,
+                 qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_add_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, const uint8_t*, size_t, uint8_t*,
+                 size_t)
+QNNP_UNSUPPORTED(qnnp_create_clamp_nc_u8, size_t, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_clamp_nc_u8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
+QNNP_UNSUPPORTED(qnnp_create_sigmoid_nc_q8, size_t, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t,
+                 qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_sigmoid_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
+QNNP_UNSUPPORTED(qnnp_create_leaky_relu_nc_q8, size_t, float, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t,
+                 qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_leaky_relu_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
+QNNP_UNSUPPORTED(qnnp_create_softargmax_nc_q8, size_t, float, uint8_t, float, uint32_t, qnnp_operator_t*)
+QNNP_UNSUPPORTED(qnnp_setup_softargmax_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
