@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native q8 hot path (contract: task statement §④ + base contract).
+
+Workload ("step"): one pass of the MobileNetV2-int8 convolution stack — 52 convolutions + classifier,
+the layer list of the reference's bench/convolution.cc:453-537 in network order, 300.8 MMAC/image —
+over a batch of 4096 synthetic 224x224x3 images PER GPU (BASELINE.json configs[4] is this stack with
+the batch sharded over GPUs; configs[1..3], the q8gemm sweep / all conv layers / the depthwise
+layers, are subsets of it and are reported from the same timed region in "q8gemm_sweep" and
+"per_kernel").  Every operator runs through the qnnpack.h C ABI of libqnnpack.so.
+
+  value    images/s, whole job, inputs resident in HBM, device-timed with CUDA events, max over ranks
+  e2e      the same through the same C-ABI calls but with the batch coming from pinned HOST memory and
+           the logits read back to the host inside the timed region
+  roofline the dominant kernel (tcgen05 implicit GEMM): algorithmic bytes / its CUDA-event time vs the
+           measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, its own SSE2 kernels and
+           operator API, pthreadpool over all host cores) on a bounded sample of the same workload
+
+Multi-GPU: one process per GPU (torchrun); the batch dimension shards, packed weights are created on
+rank 0 and broadcast once over NCCL into every rank's operators; no collective in the timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import socket
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+INT8_PEAK_TOPS_NOMINAL = 4500.0  # B200 dense int8 (task statement; not in MEASURED_PEAKS.json)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="reference arm: images per step (0 = 2 per thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified compiled reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference_stack(steps, warmup, batch, threads):
+    import numpy as np
+    from oracle import ref as R
+    from qnnpack_b200 import mobilenet_v2 as M
+
+    if not R.available():
+        raise RuntimeError("oracle/_ref/libqnnpack_ref.so is missing (build it with `make -C oracle ref`)")
+    lib = R.QnnpackHost(threads=threads)
+    stack = M.Stack(lib, seed=0)
+    cap = stack.max_activation_bytes(batch) + 64
+    x = np.random.default_rng(1).integers(0, 256, batch * 224 * 224 * 3 + 64, dtype=np.uint8)
+    a = np.zeros(cap, np.uint8)
+    b = np.zeros(cap, np.uint8)
+    stack.setup(batch, a[16:], b[16:], first_input=x[16:])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        stack.run()
+        times.append(time.perf_counter() - t0)
+    stack.delete()
+    lib.close()
+    t = times[warmup:]
+    return batch * len(t) / sum(t), sum(t) / len(t)
+
+
+def reference_main(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = args.cpu_batch or 2 * threads
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    ips, sec = run_reference_stack(steps, warmup, batch, threads)
+    line = {
+        "impl": "reference", "metric": "mobilenet_v2_int8_conv_stack_images_per_sec", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "MobileNetV2-int8 conv stack, 53 operators (BASELINE.json configs[4]; bounded CPU sample)",
+                   "batch_per_step": batch, "threads": threads},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "reference",
+                         "sample": f"{steps} passes of the full 53-operator stack over {batch} images, "
+                                   f"unmodified reference (SSE2 ukernels) via oracle/_ref with a {threads}-thread pthreadpool"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class DevMem:
+    """Raw device memory as a __cuda_array_interface__ object (for torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def b200_main(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    os.environ["QNNP_CUDA_DEVICE"] = str(local_rank)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import qnnpack_b200
+    from qnnpack_b200 import mobilenet_v2 as M
+
+    lib = qnnpack_b200.load()  # raises if the extension or the GPU is missing: no fallback
+    stream = torch.cuda.current_stream()
+    lib.set_stream(stream.cuda_stream)
+
+    B = args.batch
+    stack = M.Stack(lib, seed=0, zero_weights=(rank != 0))
+    # one-time replication of the packed weights: rank 0 -> all, over NCCL (NVLink/NVSwitch)
+    bcast_bytes = 0
+    if world > 1:
+        for op in stack.ops:
+            for ptr, n in (lib.packed_weights(op), lib.packed_bias(op)):
+                t = torch.as_tensor(DevMem(ptr, n), device=dev)
+                dist.broadcast(t, src=0)
+                bcast_bytes += n
+        torch.cuda.synchronize()
+
+    cap = stack.max_activation_bytes(B)
+    x_in = torch.randint(0, 256, (B * 224 * 224 * 3,), dtype=torch.uint8, device=dev)
+    buf_a = torch.empty(cap, dtype=torch.uint8, device=dev)
+    buf_b = torch.empty(cap, dtype=torch.uint8, device=dev)
+    final = stack.setup(B, buf_a.data_ptr(), buf_b.data_ptr(), first_input=x_in.data_ptr())
+    logits_dev = (buf_a, buf_b)[final][: B * 1000]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nl = len(stack.layers)
+    for _ in range(args.warmup):
+        stack.run(asynchronous=True)
+    barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM ------------------------------------------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(nl + 1)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.launch_count()
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record(stream)
+        stack.run(asynchronous=True, hook=lambda i, after, s=s: ev[s][i + 1].record(stream) if after else None)
+    barrier()
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = ev[0][0].elapsed_time(ev[-1][nl])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # per-layer times (mean over steps) from the same timed region
+    layer_ms = [statistics.fmean(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)) for i in range(nl)]
+
+    # ---- e2e: batch from pinned host memory, logits back to the host, inside the timed region ---------
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.randint(0, 256, (B * 224 * 224 * 3,), dtype=torch.uint8).pin_memory()
+        y_host = torch.empty(B * 1000, dtype=torch.uint8).pin_memory()
+
+        def e2e_step():
+            x_in.copy_(x_host, non_blocking=True)
+            stack.run(asynchronous=True)
+            y_host.copy_(logits_dev, non_blocking=True)
+            stream.synchronize()  # the caller owns the result when the call returns
+
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * args.steps / (float(t.item()) * 1e-3), "unit": "images/s",
+               "h2d_bytes_per_step": int(x_host.numel()), "d2h_bytes_per_step": int(y_host.numel())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- reporting (rank 0) -----------------------------------------------------------------------------
+    peak_gbs, peak_src = measured_peaks()
+    kinds = {"igemm": ("conv", "pw", "fc"), "dwconv3x3": ("dw",)}
+    per_kernel = {}
+    for kname, ks in kinds.items():
+        idx = [i for i, l in enumerate(stack.layers) if l.kind in ks]
+        ms = sum(layer_ms[i] for i in idx)
+        by = sum(stack.layers[i].algorithmic_bytes(B) for i in idx)
+        ops = sum(stack.layers[i].ops(B) for i in idx)
+        per_kernel[kname] = {"launches_per_step": len(idx), "ms_per_step": ms, "share_of_step": ms / sum(layer_ms),
+                             "algorithmic_gb": by / 1e9, "achieved_gbs": by / 1e6 / ms, "frac_of_hbm_peak": by / 1e6 / ms / peak_gbs,
+                             "tops": ops / 1e9 / ms}
+    ig = per_kernel["igemm"]
+    roofline = {"kernel": "q8_igemm_kernel (tcgen05 kind::i8 implicit GEMM, fused Q31 epilogue)", "bound": "hbm",
+                "achieved": ig["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": ig["achieved_gbs"] / peak_gbs,
+                "traffic": None, "peak_source": peak_src,
+                "note": "achieved = sum of algorithmic bytes of the %d igemm launches of a step / sum of their CUDA-event "
+                        "durations in the timed region" % ig["launches_per_step"]}
+    # BASELINE.json configs[1]: q8gemm sweep = the distinct 1x1 / FC shapes, each once
+    seen, sw_ops, sw_ms, sweep_rows = set(), 0.0, 0.0, []
+    for i, l in enumerate(stack.layers):
+        if l.kind in ("pw", "fc") and (l.h, l.cin, l.cout) not in seen:
+            seen.add((l.h, l.cin, l.cout))
+            sw_ops += l.ops(B); sw_ms += layer_ms[i]
+            bound_ms = max(l.ops(B) / (INT8_PEAK_TOPS_NOMINAL * 1e9), l.algorithmic_bytes(B) / (peak_gbs * 1e6))
+            sweep_rows.append({"layer": l.name, "m": B * l.out_h * l.out_h if l.kind != "fc" else B, "n": l.cout, "k": l.cin,
+                               "ms": layer_ms[i], "tops": l.ops(B) / 1e9 / layer_ms[i],
+                               "gbs": l.algorithmic_bytes(B) / 1e6 / layer_ms[i], "frac_of_roofline": bound_ms / layer_ms[i]})
+    q8gemm = {"tops": sw_ops / 1e9 / sw_ms, "pct_of_int8_peak_nominal": 100.0 * sw_ops / 1e9 / sw_ms / INT8_PEAK_TOPS_NOMINAL,
+              "int8_peak_tops_nominal": INT8_PEAK_TOPS_NOMINAL, "shapes": sweep_rows}
+    layers_out = [{"layer": l.name, "kind": l.kind, "ms": layer_ms[i], "gbs": l.algorithmic_bytes(B) / 1e6 / layer_ms[i],
+                   "tops": l.ops(B) / 1e9 / layer_ms[i]} for i, l in enumerate(stack.layers)]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            cb = args.cpu_batch or 2 * threads
+            ips, sec = run_reference_stack(3, 1, cb, threads)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "reference",
+                   "sample": f"3 passes of the full 53-operator stack over {cb} images, unmodified reference "
+                             f"(oracle/_ref, SSE2 ukernels) with a {threads}-thread pthreadpool"}
+        except Exception as exc:  # the baseline is informative; never let it take the GPU numbers down
+            cpu = {"value": None, "unit": "images/s", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
+
+    line = {
+        "metric": "mobilenet_v2_int8_conv_stack_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "MobileNetV2-int8 conv stack (53 operators, 300.8 MMAC/image; BASELINE.json configs[4], "
+                               "containing the q8gemm sweep configs[1], all conv layers configs[2] and the depthwise layers configs[3])",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "every layer streams activations far larger than the 126 MB L2 (no flush needed)",
+                   "quantization": "zero points 127, requant scale 1/(128*sqrt(K)), clamp 0..255",
+                   "weights_broadcast_bytes": bcast_bytes},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "q8gemm_sweep": q8gemm, "per_kernel": per_kernel, "layers": layers_out,
+        "stack_ops_g": stack.total_ops(B) / 1e9, "stack_algorithmic_gb": stack.total_bytes(B) / 1e9,
+        "stack_frac_of_hbm_roofline": (stack.total_bytes(B) / 1e6 / peak_gbs) / ms_per_step,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_main(args, rank, world)
+    else:
+        b200_main(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

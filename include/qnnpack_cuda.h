@@ -31,6 +31,8 @@ enum qnnp_status qnnp_cuda_run_operator_async(qnnp_operator_t op);
  * torch.distributed.broadcast over NVLink) into the identically-created operator on every rank;
  * the steady-state run has no collective.  Returns qnnp_status_invalid_parameter for NULL. */
 enum qnnp_status qnnp_cuda_operator_packed_weights(qnnp_operator_t op, void** device_ptr, size_t* size_bytes);
+/* The folded int32 bias (b + K*izp*kzp - izp*sum w, reference src/qnnpack/pack.h:24-43) that goes with it. */
+enum qnnp_status qnnp_cuda_operator_packed_bias(qnnp_operator_t op, void** device_ptr, size_t* size_bytes);
 
 /* Number of kernels the library has launched since qnnp_initialize() (bench.py's gpu_launches). */
 unsigned long long qnnp_cuda_launch_count(void);

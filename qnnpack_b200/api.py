@@ -61,6 +61,7 @@ class QnnpackLibrary:
             L.qnnp_cuda_get_stream.restype = C.c_void_p
             L.qnnp_cuda_run_operator_async.argtypes = [C.c_void_p]
             L.qnnp_cuda_operator_packed_weights.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+            L.qnnp_cuda_operator_packed_bias.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
             L.qnnp_cuda_requantize_q31.argtypes = [C.c_size_t, C.c_void_p, C.c_float, C.c_uint8, C.c_uint8, C.c_uint8,
                                                    C.c_void_p]
             L.qnnp_cuda_debug_set_accumulator_dump.argtypes = [C.c_void_p]
@@ -127,6 +128,18 @@ class QnnpackLibrary:
         if st != 0:
             raise QnnpackError("qnnp_cuda_operator_packed_weights", st)
         return p.value, n.value
+
+    def packed_bias(self, op):
+        p, n = C.c_void_p(), C.c_size_t()
+        st = self.lib.qnnp_cuda_operator_packed_bias(op, C.byref(p), C.byref(n))
+        if st != 0:
+            raise QnnpackError("qnnp_cuda_operator_packed_bias", st)
+        return p.value, n.value
+
+    def set_stream(self, cuda_stream: int):
+        st = self.lib.qnnp_cuda_set_stream(C.c_void_p(cuda_stream))
+        if st != 0:
+            raise QnnpackError("qnnp_cuda_set_stream", st)
 
     # -- one-shot helpers on host arrays ------------------------------------------------------
     def convolution(self, x, kernel, bias, *, out_stride=None, out_fill=0xA5, lead_in=16, **kw):

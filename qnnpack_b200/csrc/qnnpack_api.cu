@@ -102,6 +102,12 @@ void init_once() {
   g_lib.init_status = qnnp_status_success;
 }
 
+// The CUDA "current device" is per thread; callers may come from any thread.
+void bind_device() {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != g_lib.device) cudaSetDevice(g_lib.device);
+}
+
 bool is_device_pointer(const void* ptr) {
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
@@ -409,6 +415,7 @@ enum qnnp_status ensure_capacity(uint8_t** buf, size_t* cap, size_t need) {
 enum qnnp_status run_impl(qnnp_operator* op, bool async) {
   if (op == nullptr) return qnnp_status_invalid_parameter;
   if (op->batch == 0) return qnnp_status_success;  // src/operator-run.c:642
+  bind_device();
   cudaStream_t stream = g_lib.stream;
   if (op->in_on_device && op->out_on_device) {
     enum qnnp_status st = launch(op, op->input, op->output, stream);
@@ -518,6 +525,7 @@ QNNP_EXPORT enum qnnp_status qnnp_create_convolution2d_nhwc_q8(
     return qnnp_status_invalid_parameter;
   }
 
+  bind_device();
   qnnp_operator* op = new (std::nothrow) qnnp_operator();
   if (op == nullptr) return qnnp_status_out_of_memory;
   op->pad_top = input_padding_top, op->pad_right = input_padding_right;
@@ -600,6 +608,7 @@ QNNP_EXPORT enum qnnp_status qnnp_create_fully_connected_nc_q8(
     return qnnp_status_unsupported_parameter;
   }
   if (input_channels == 0 || output_channels == 0) return qnnp_status_invalid_parameter;
+  bind_device();
   qnnp_operator* op = new (std::nothrow) qnnp_operator();
   if (op == nullptr) return qnnp_status_out_of_memory;
   op->is_fc = true;
@@ -662,6 +671,12 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_weights(qnnp_operator_t o
   *size_bytes = op->weights_bytes;
   return qnnp_status_success;
 }
+QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_bias(qnnp_operator_t op, void** device_ptr, size_t* size_bytes) {
+  if (op == nullptr || device_ptr == nullptr || size_bytes == nullptr) return qnnp_status_invalid_parameter;
+  *device_ptr = op->d_bias;
+  *size_bytes = op->bias_count * sizeof(int32_t);
+  return qnnp_status_success;
+}
 QNNP_EXPORT unsigned long long qnnp_cuda_launch_count(void) { return g_lib.launches.load(); }
 QNNP_EXPORT void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer) { g_lib.dbg_acc = device_buffer; }
 QNNP_EXPORT const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op) {
@@ -680,6 +695,7 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_requantize_q31(
   if (!g_lib.initialized) return qnnp_status_uninitialized;
   if (!(scale < 1.0f) || !(scale >= 0x1.0p-32f)) return qnnp_status_unsupported_parameter;
   if (n == 0) return qnnp_status_success;
+  bind_device();
   const Q8Requant rq = q8_make_requant(f32_bits(scale), zero_point, qmin, qmax);
   cudaStream_t stream = g_lib.stream;
   const bool in_dev = is_device_pointer(input), out_dev = is_device_pointer(output);

@@ -1,0 +1,191 @@
+"""MobileNetV2-int8 convolution stack as a workload for any qnnpack.h implementation.
+
+Layer shapes: reference bench/convolution.cc:453-537 (the distinct layers) unrolled into network order
+with the (t, c, n, s) table of the architecture: 52 convolutions + the 1280->1000 classifier = 53
+operators, 300.8 MMAC per 224x224 image.  Residual adds and the global average pool are not
+convolutions and are outside the q8gemm/q8conv/q8dwconv path.
+
+Quantisation of the synthetic network: input/kernel zero points 127 as in the reference benches
+(bench/convolution.cc:64-76, bench/q8gemm.cc:95-103); weights uniform uint8, bias uniform
+[-10000, 10000]; the requantisation scale of each layer is 1/(128*sqrt(K)) so that outputs spread over
+the uint8 range instead of saturating (the benches' 0.5*0.5/0.5 saturates nearly every output and is
+far from any real network's scale).  Output clamp [0, 255].
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Layer:
+    name: str
+    kind: str          # "conv" (groups=1, kxk), "pw" (1x1), "dw" (3x3 depthwise), "fc"
+    h: int             # input height = width
+    cin: int
+    cout: int
+    k: int
+    stride: int
+
+    @property
+    def groups(self):
+        return self.cin if self.kind == "dw" else 1
+
+    @property
+    def gic(self):
+        return 1 if self.kind == "dw" else self.cin
+
+    @property
+    def goc(self):
+        return 1 if self.kind == "dw" else self.cout
+
+    @property
+    def pad(self):
+        return self.k // 2
+
+    @property
+    def out_h(self):
+        return (self.h + 2 * self.pad - self.k) // self.stride + 1
+
+    @property
+    def k_eff(self):
+        return self.k * self.k * self.gic
+
+    def ops(self, batch):
+        """2*M*N*K_eff, the reference's own counter (bench/convolution.cc:99-104, bench/q8gemm.cc:108)."""
+        m = batch * self.out_h * self.out_h if self.kind != "fc" else batch
+        return 2 * m * self.cout * self.k_eff
+
+    def algorithmic_bytes(self, batch):
+        """input read once + weights/bias + output written once; int32 never counts."""
+        if self.kind == "fc":
+            return batch * self.cin + self.cout * (self.cin + 4) + batch * self.cout
+        return (batch * self.h * self.h * self.cin + self.cout * (self.k_eff + 4)
+                + batch * self.out_h * self.out_h * self.cout)
+
+
+def layers() -> list[Layer]:
+    seq = [Layer("stem", "conv", 224, 3, 32, 3, 2)]
+    h, c = 112, 32
+    idx = 1
+    for t, cout, n, s in ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+                          (6, 320, 1, 1)):
+        for i in range(n):
+            stride = s if i == 0 else 1
+            hidden = c * t
+            if t != 1:
+                seq.append(Layer(f"b{idx}_expand", "pw", h, c, hidden, 1, 1))
+            seq.append(Layer(f"b{idx}_dw", "dw", h, hidden, hidden, 3, stride))
+            h = (h + 2 - 3) // stride + 1
+            seq.append(Layer(f"b{idx}_project", "pw", h, hidden, cout, 1, 1))
+            c = cout
+            idx += 1
+    seq.append(Layer("last_1x1", "pw", h, c, 1280, 1, 1))
+    seq.append(Layer("classifier", "fc", 1, 1280, 1000, 1, 1))
+    return seq
+
+
+def gemm_sweep() -> list[Layer]:
+    """BASELINE.json configs[1]: the distinct 1x1-bottleneck GEMM shapes (+ classifier), each once."""
+    seen, out = set(), []
+    for l in layers():
+        if l.kind in ("pw", "fc"):
+            key = (l.h, l.cin, l.cout)
+            if key not in seen:
+                seen.add(key)
+                out.append(l)
+    return out
+
+
+def requant_scale(layer: Layer) -> float:
+    return float(np.float32(1.0 / (128.0 * math.sqrt(layer.k_eff))))
+
+
+def layer_params(layer: Layer, seed: int):
+    """-> (kernel uint8, bias int32, create-kwargs) for qnnpack_b200.api.QnnpackLibrary."""
+    rng = np.random.default_rng(seed)
+    if layer.kind == "fc":
+        kernel = rng.integers(0, 256, (layer.cout, layer.cin), dtype=np.uint8)
+    else:
+        kernel = rng.integers(0, 256, (layer.groups, layer.goc, layer.k, layer.k, layer.gic), dtype=np.uint8)
+    bias = rng.integers(-10000, 10001, (layer.cout,), dtype=np.int32)
+    q = dict(izp=127, input_scale=1.0, kzp=127, kernel_scale=requant_scale(layer), ozp=127, output_scale=1.0,
+             qmin=0, qmax=255)
+    if layer.kind == "fc":
+        return kernel, bias, q
+    p = layer.pad
+    return kernel, bias, dict(pad=(p, p, p, p), ksize=(layer.k, layer.k), stride=(layer.stride, layer.stride),
+                              dilation=(1, 1), groups=layer.groups, gic=layer.gic, goc=layer.goc, **q)
+
+
+class Stack:
+    """The 53 operators created once through the C ABI; activations ping-pong between two buffers
+    that the caller provides (device addresses for the product, NumPy arrays for the reference)."""
+
+    def __init__(self, lib, seed: int = 0, zero_weights: bool = False, only=None):
+        self.lib = lib
+        self.layers = layers() if only is None else only
+        self.ops = []
+        for i, l in enumerate(self.layers):
+            kernel, bias, kw = layer_params(l, seed * 1000 + i)
+            if zero_weights:  # ranks > 0: real weights arrive by broadcast of the packed blobs
+                kernel, bias = np.zeros_like(kernel), np.zeros_like(bias)
+            if l.kind == "fc":
+                st, op = lib.create_fully_connected(kernel, bias, **kw)
+            else:
+                st, op = lib.create_convolution(kernel, bias, **kw)
+            if st != 0:
+                raise RuntimeError(f"create {l.name} -> status {st}")
+            self.ops.append(op)
+
+    def max_activation_bytes(self, batch):
+        m = 0
+        for l in self.layers:
+            if l.kind == "fc":
+                m = max(m, batch * l.cin, batch * l.cout)
+            else:
+                m = max(m, batch * l.h * l.h * l.cin, batch * l.out_h * l.out_h * l.cout)
+        return m
+
+    def setup(self, batch, buf_a, buf_b, first_input=None):
+        """Chains the operators through two ping-pong activation buffers (device addresses as int, or
+        uint8 NumPy arrays, each of at least max_activation_bytes(batch)).  With ``first_input`` the first
+        layer reads that (never overwritten) buffer and writes buf_a; otherwise it reads buf_a and writes
+        buf_b.  Returns 0 if the final output lies in buf_a, 1 if in buf_b."""
+        bufs = (buf_a, buf_b)
+        shift = 1 if first_input is not None else 0
+        where = 0
+        for i, (l, op) in enumerate(zip(self.layers, self.ops)):
+            src = first_input if (i == 0 and first_input is not None) else bufs[(i - shift) % 2]
+            where = (i - shift + 1) % 2
+            dst = bufs[where]
+            if l.kind == "fc":
+                st = self.lib.setup_fully_connected(op, batch, src, l.cin, dst, l.cout)
+            else:
+                st = self.lib.setup_convolution(op, batch, l.h, l.h, src, l.cin, dst, l.cout)
+            if st != 0:
+                raise RuntimeError(f"setup {l.name} -> status {st}")
+        return where
+
+    def run(self, asynchronous=False, hook=None):
+        for i, op in enumerate(self.ops):
+            if hook is not None:
+                hook(i, 0)
+            st = self.lib.run_async(op) if asynchronous else self.lib.run(op)
+            if st != 0:
+                raise RuntimeError(f"run {self.layers[i].name} -> status {st}")
+            if hook is not None:
+                hook(i, 1)
+
+    def delete(self):
+        for op in self.ops:
+            self.lib.delete(op)
+        self.ops = []
+
+    def total_ops(self, batch):
+        return sum(l.ops(batch) for l in self.layers)
+
+    def total_bytes(self, batch):
+        return sum(l.algorithmic_bytes(batch) for l in self.layers)
