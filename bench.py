@@ -153,13 +153,6 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-class DevMem:
-    """Raw device memory as a __cuda_array_interface__ object (for torch.as_tensor)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-
-
 def b200_main(args, rank, local_rank, world):
     import numpy as np
     import torch
@@ -175,7 +168,11 @@ def b200_main(args, rank, local_rank, world):
     from qnnpack_b200 import mobilenet_v2 as M
 
     lib = qnnpack_b200.load()  # raises if the extension or the GPU is missing: no fallback
-    stream = torch.cuda.current_stream()
+    # A dedicated (non-default) stream carries every launch, copy and event of the benchmark; the
+    # library is told to enqueue on it (NULL would select the library's own stream instead).
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     lib.set_stream(stream.cuda_stream)
 
     B = args.batch
@@ -183,11 +180,10 @@ def b200_main(args, rank, local_rank, world):
     # one-time replication of the packed weights: rank 0 -> all, over NCCL (NVLink/NVSwitch)
     bcast_bytes = 0
     if world > 1:
-        for op in stack.ops:
-            for ptr, n in (lib.packed_weights(op), lib.packed_bias(op)):
-                t = torch.as_tensor(DevMem(ptr, n), device=dev)
-                dist.broadcast(t, src=0)
-                bcast_bytes += n
+        from qnnpack_b200 import shard as S
+        blobs = [torch.as_tensor(S.DeviceBytes(ptr, n), device=dev)
+                 for op in stack.ops for ptr, n in (lib.packed_weights(op), lib.packed_bias(op))]
+        bcast_bytes = S.replicate_from_rank0(blobs)
         torch.cuda.synchronize()
 
     cap = stack.max_activation_bytes(B)
