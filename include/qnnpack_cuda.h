@@ -48,6 +48,12 @@ enum qnnp_status qnnp_cuda_requantize_q31(
  * their raw int32 accumulators ([work item][128][n_mma]) to this DEVICE buffer. */
 void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer);
 
+/* The tiling / shared-memory plan the tensor-core kernel would use for a K x N (x groups) operator; needs no GPU.
+ * out = {K, nkc, skc, k_stages, mt, n_tiles, n_tile, n_mma, has_corr, b_resident, num_stages, stage_bytes,
+ *        staging_bytes, bias_bytes, smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, smem_total, bulk_capable}.
+ * Returns 1 on success, 0 if no plan fits. */
+int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int out[20]);
+
 /* Name of the kernel family an operator was routed to: "igemm-gemm", "igemm-conv", "dwconv3x3", "direct". */
 const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op);
 

@@ -24,13 +24,17 @@ namespace q8 {
 template <int RQ>
 __device__ __forceinline__ int32_t requant_one(int32_t n, const Q8Requant& rq) {
   if constexpr (RQ == 0) {
-    return q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.c_neg, rq.shift - 1);
+    return q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
   } else if constexpr (RQ == 1) {
-    int32_t t = q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.c_neg, rq.shift - 1);
+    int32_t t = q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
     t = max(t, rq.qmin);
     return min(t, rq.qmax);
   } else if constexpr (RQ == 2) {
     return q8_requant_shift0(n, rq.multiplier, rq.zero_point, rq.qmin, rq.qmax);
+  } else if constexpr (RQ == 4) {
+    int32_t t = q8_requant_fused_shift1_unclamped(n, rq.multiplier, rq.c_neg);
+    t = max(t, rq.qmin);
+    return min(t, rq.qmax);
   } else {
     return q8_requant_exact_slow(n, rq);
   }
@@ -147,6 +151,7 @@ static cudaError_t launch_dw_rq(const DwParams& p, cudaStream_t stream) {
     case 0: q8_dwconv3x3_kernel<CV, SW, TX, 0><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     case 1: q8_dwconv3x3_kernel<CV, SW, TX, 1><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     case 2: q8_dwconv3x3_kernel<CV, SW, TX, 2><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
+    case 4: q8_dwconv3x3_kernel<CV, SW, TX, 4><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     default: q8_dwconv3x3_kernel<CV, SW, TX, 3><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
   }
   return cudaGetLastError();

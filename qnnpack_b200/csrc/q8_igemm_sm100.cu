@@ -13,13 +13,16 @@
 // which lets the tensor core run raw u8 x u8 -> s32.  sum_k a[m][k] falls out of the same UMMA as one
 // extra B row of ones (accumulator column n_tile).
 //
-// Structure (one CTA per SM, 416 threads):
-//   warps 0-3  epilogue group 0   TMEM -> regs -> Q31 requant -> uint8 -> global   (even work items)
-//   warps 4-7  epilogue group 1                                                    (odd work items)
-//   warp  8    TMEM allocation + UMMA issue (one lane)
-//   warps 9-12 loaders: cp.async global -> smem, canonical K-major no-swizzle layout [k-chunk][row][16 B]
+// Structure (one CTA per SM, 672 threads):
+//   warps 0-7   epilogue pair 0 (TMEM stage 0, even work items)   TMEM -> regs -> Q31 requant -> uint8 -> global
+//   warps 8-15  epilogue pair 1 (TMEM stage 1, odd work items)
+//   warp  16    TMEM allocation + UMMA issue (one lane)
+//   warps 17-20 loaders: cp.async global -> smem, canonical K-major no-swizzle layout [sub-tile][k-chunk][row][16 B]
+// A work item is `mt` (<= 8) consecutive 128-row sub-tiles x one n-tile: the sub-tiles' accumulators sit side
+// by side in one TMEM stage (mt * n_mma <= 256 columns), which amortises every per-item synchronisation
+// over up to 1024 rows — essential for the narrow (N = 16..96) projection layers.
 // Pipelines: smem ring full/empty mbarriers (loaders <-> UMMA), two TMEM accumulator stages
-// full/empty (UMMA <-> epilogue groups).  int32 accumulators never leave TMEM/registers.
+// full/empty (UMMA <-> epilogue pairs).  int32 accumulators never leave TMEM/registers.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,12 +31,13 @@
 
 namespace q8 {
 
-constexpr int kEpiWarps = 8;
-constexpr int kMmaWarp = 8;
-constexpr int kLoadWarp0 = 9;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiPairThreads = 256;
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kLoadWarp0 = kMmaWarp + 1;
 constexpr int kLoadWarps = 4;
 constexpr int kLoadThreads = kLoadWarps * 32;
-constexpr int kThreads = (kLoadWarp0 + kLoadWarps) * 32;  // 416
+constexpr int kThreads = (kLoadWarp0 + kLoadWarps) * 32;  // 672
 constexpr int kTmemCols = 512;
 
 struct __align__(8) SmemCtl {
@@ -46,16 +50,20 @@ struct __align__(8) SmemCtl {
 };
 
 struct Item {
-  long long m0;
+  long long m0;  // first row of the item
   int g, nt;
+  int mt_eff;    // sub-tiles that contain at least one valid row
 };
 
 __device__ __forceinline__ Item decode_item(const IgemmParams& p, long long item) {
   Item it;
   it.nt = (int) (item % p.n_tiles);
   const long long rest = item / p.n_tiles;
-  it.m0 = (rest % p.m_tiles) * kTileM;
-  it.g = (int) (rest / p.m_tiles);
+  const long long st = rest % p.m_super;
+  it.g = (int) (rest / p.m_super);
+  it.m0 = st * p.mt * kTileM;
+  const long long left = p.m_tiles - st * p.mt;
+  it.mt_eff = left < p.mt ? (int) left : p.mt;
   return it;
 }
 
@@ -97,13 +105,14 @@ __device__ __forceinline__ void load_a_gemm(const IgemmParams& p, const Item& it
   const int lane = ltid & 31, lw = ltid >> 5;
   const int rsub = lane & 7, psub = lane >> 3;
   const uint8_t* base = p.in + (size_t) it.g * p.gic + k0;
+  const int rows = it.mt_eff * kTileM;
+  const uint32_t sub_bytes = (uint32_t) p.skc * kChunkBytes;
 #pragma unroll 1
-  for (int rb = lw * 8; rb < kTileM; rb += kLoadWarps * 8) {
-    const int row = rb + rsub;
-    const long long m = it.m0 + row;
+  for (int rr = lw * 8 + rsub; rr < rows; rr += kLoadWarps * 8) {
+    const long long m = it.m0 + rr;
     if (m < p.M) {
       const uint8_t* src = base + (size_t) m * p.in_stride;
-      const uint32_t drow = a_stage + row * 16;
+      const uint32_t drow = a_stage + (uint32_t) (rr >> 7) * sub_bytes + (uint32_t) (rr & 127) * 16;
 #pragma unroll 2
       for (int pc = psub; pc < pps; pc += 4) {
         const int kr = pc * VEC;
@@ -118,37 +127,38 @@ __device__ __forceinline__ void load_a_gemm(const IgemmParams& p, const Item& it
 // (src/indirection.c:56-63); out-of-bounds taps are filled with the byte izp (src/convolution.c:336).
 template <int VEC>
 __device__ __forceinline__ void load_a_conv(const IgemmParams& p, const Item& it, int ks, uint32_t a_stage, int ltid) {
-  const int row = ltid;
-  const long long m = it.m0 + row;
-  if (m < p.M) {  // (no early return: every loader thread must still arrive on the stage barrier)
-    const int k0 = ks * p.skc * 16;
-    int k1 = k0 + p.skc * 16;
-    k1 = k1 < p.K ? k1 : p.K;
-    const int ox = (int) (m % p.out_w);
-    const long long t = m / p.out_w;
-    const int oy = (int) (t % p.out_h);
-    const long long n = t / p.out_h;
-    const int iy0 = oy * p.stride_h - p.pad_top, ix0 = ox * p.stride_w - p.pad_left;
-    const int tap = k0 / p.gic;
-    int c = k0 % p.gic;
-    int ky = tap / p.kw, kx = tap % p.kw;
-    const uint32_t drow = a_stage + row * 16;
-    const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
-    const uint8_t* img = p.in + (size_t) n * p.in_h * p.in_w * p.in_stride + (size_t) it.g * p.gic;
-    for (int kr = 0; kr < k1 - k0; kr += VEC) {
-      const int iy = iy0 + ky * p.dil_h, ix = ix0 + kx * p.dil_w;
-      const uint32_t dst = drow + (kr >> 4) * kChunkBytes + (kr & 15);
-      if ((unsigned) iy < (unsigned) p.in_h && (unsigned) ix < (unsigned) p.in_w) {
-        copy_piece<VEC>(dst, img + ((size_t) iy * p.in_w + ix) * p.in_stride + c);
-      } else {
-        fill_piece<VEC>(dst, fill);
-      }
-      c += VEC;
-      if (c >= p.gic) {
-        c = 0;
-        if (++kx == p.kw) {
-          kx = 0;
-          ++ky;
+  const int k0 = ks * p.skc * 16;
+  int k1 = k0 + p.skc * 16;
+  k1 = k1 < p.K ? k1 : p.K;
+  const int tap0 = k0 / p.gic, c0 = k0 % p.gic;
+  const int ky0 = tap0 / p.kw, kx0 = tap0 % p.kw;
+  const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
+  for (int j = 0; j < it.mt_eff; j++) {
+    const long long m = it.m0 + (long long) j * kTileM + ltid;
+    if (m < p.M) {  // (no early exit: every loader thread must still arrive on the stage barrier)
+      const int ox = (int) (m % p.out_w);
+      const long long t = m / p.out_w;
+      const int oy = (int) (t % p.out_h);
+      const long long n = t / p.out_h;
+      const int iy0 = oy * p.stride_h - p.pad_top, ix0 = ox * p.stride_w - p.pad_left;
+      int c = c0, ky = ky0, kx = kx0;
+      const uint32_t drow = a_stage + (uint32_t) (j * p.skc) * kChunkBytes + (uint32_t) ltid * 16;
+      const uint8_t* img = p.in + (size_t) n * p.in_h * p.in_w * p.in_stride + (size_t) it.g * p.gic;
+      for (int kr = 0; kr < k1 - k0; kr += VEC) {
+        const int iy = iy0 + ky * p.dil_h, ix = ix0 + kx * p.dil_w;
+        const uint32_t dst = drow + (kr >> 4) * kChunkBytes + (kr & 15);
+        if ((unsigned) iy < (unsigned) p.in_h && (unsigned) ix < (unsigned) p.in_w) {
+          copy_piece<VEC>(dst, img + ((size_t) iy * p.in_w + ix) * p.in_stride + c);
+        } else {
+          fill_piece<VEC>(dst, fill);
+        }
+        c += VEC;
+        if (c >= p.gic) {
+          c = 0;
+          if (++kx == p.kw) {
+            kx = 0;
+            ++ky;
+          }
         }
       }
     }
@@ -170,13 +180,17 @@ __device__ __forceinline__ uint32_t requant4(const int32_t* v, const IgemmParams
   for (int i = 0; i < 4; i++) {
     const int32_t n = v[i] + bb[i] + corr;
     if constexpr (RQ == 0) {
-      y[i] = q8_requant_fused_unclamped(n, p.rq.multiplier, p.rq.c_pos, p.rq.c_neg, p.rq.shift - 1);
+      y[i] = q8_requant_fused_unclamped(n, p.rq.multiplier, p.rq.c_pos, p.rq.shift - 1);
     } else if constexpr (RQ == 1) {
-      int32_t t = q8_requant_fused_unclamped(n, p.rq.multiplier, p.rq.c_pos, p.rq.c_neg, p.rq.shift - 1);
+      int32_t t = q8_requant_fused_unclamped(n, p.rq.multiplier, p.rq.c_pos, p.rq.shift - 1);
       t = max(t, p.rq.qmin);
       y[i] = min(t, p.rq.qmax);
     } else if constexpr (RQ == 2) {
       y[i] = q8_requant_shift0(n, p.rq.multiplier, p.rq.zero_point, p.rq.qmin, p.rq.qmax);
+    } else if constexpr (RQ == 4) {
+      int32_t t = q8_requant_fused_shift1_unclamped(n, p.rq.multiplier, p.rq.c_neg);
+      t = max(t, p.rq.qmin);
+      y[i] = min(t, p.rq.qmax);
     } else {
       y[i] = q8_requant_exact_slow(n, p.rq);
     }
@@ -184,67 +198,86 @@ __device__ __forceinline__ uint32_t requant4(const int32_t* v, const IgemmParams
   return pack_sat_u8x4(y[0], y[1], y[2], y[3]);  // saturation to [0,255] is the clamp when qmin=0,qmax=255
 }
 
-// store up to 16 output bytes (4 packed words) of one row with the widest legal accesses
-__device__ __forceinline__ void store_row16(uint8_t* dst, const uint32_t (&w)[4], int valid, int vec) {
-  if (valid >= 16 && vec >= 16) {
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    return;
-  }
+// Slow path of the direct store: fewer than 16 valid bytes, or a destination that is not 16-byte aligned.
+__device__ __noinline__ void store_row_partial(uint8_t* dst, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int valid,
+                                               int vec) {
+  const uint32_t w[4] = {w0, w1, w2, w3};
+  int i = 0;
   if (vec >= 4) {
-    const int full = valid >> 2;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (i < full) reinterpret_cast<uint32_t*>(dst)[i] = w[i];
-    for (int i = full * 4; i < valid; i++) dst[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
-    return;
+    for (; i + 4 <= valid; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = w[i >> 2];
   }
-  for (int i = 0; i < valid; i++) dst[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
+  for (; i < valid; i++) dst[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
 }
 
+__device__ __noinline__ void dump_acc(const IgemmParams& p, long long item, int j, int row, int c0, const int32_t* v,
+                                      int32_t rowsum) {
+  int32_t* d = p.dbg_acc + (((size_t) item * p.mt + j) * kTileM + row) * p.n_mma;
+  for (int i = 0; i < 16; i++) d[c0 + i] = v[i];
+  if (c0 == 0 && p.has_corr) d[p.n_tile] = rowsum;
+}
+
+// One epilogue warp: lane quarter q = warp % 4 of the accumulator, every second (sub-tile, 16-column) unit.
 template <int RQ>
 __device__ __forceinline__ void epilogue_item(
-    const IgemmParams& p, const Item& it, long long item, uint32_t tmem_acc, int grp_tid, uint32_t staging, bool bulk) {
-  const int row = grp_tid;  // == 32*(warp%4) + lane == TMEM lane
-  const long long m = it.m0 + row;
-  const uint32_t tlane = tmem_acc + ((uint32_t) (row & ~31) << 16);
-  int32_t rowsum;
-  tmem_ld1(tlane + p.n_tile, rowsum);
-  tmem_ld_wait();
-  const int32_t corr = -p.kzp * rowsum;
+    const IgemmParams& p, const Item& it, long long item, uint32_t tmem_acc, int q, int half, int lane, uint32_t bias_smem,
+    uint32_t staging, bool bulk) {
+  const int row = q * 32 + lane;  // TMEM lane == row inside a sub-tile
+  const uint32_t tlane = tmem_acc + ((uint32_t) (q * 32) << 16);
+  const int ch = p.n_tile >> 4;   // 16-column chunks per sub-tile
+  const int units = it.mt_eff * ch;
   const int n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
-  const int32_t* bias = p.bias + ((size_t) it.g * p.n_tiles + it.nt) * p.n_tile;
-  uint8_t* orow = p.out + (size_t) m * p.out_stride + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
-  const uint32_t srow = staging + row * p.goc;
+  const uint32_t bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
+  uint8_t* const obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
 
-  for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+  int j = half / ch, c = half - j * ch;
+  for (int u = half; u < units; u += 2) {
+    const int c0 = c << 4;
     int32_t v[16];
-    tmem_ld16(tlane + c0, v);
+    int32_t rowsum = 0;
+    tmem_ld16(tlane + j * p.n_mma + c0, v);
+    if (p.has_corr) tmem_ld1(tlane + j * p.n_mma + p.n_tile, rowsum);
+    int4 b[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(b[t].x), "=r"(b[t].y), "=r"(b[t].z), "=r"(b[t].w)
+                   : "r"(bias_base + (uint32_t) (c0 + 4 * t) * 4));
     tmem_ld_wait();
-    if (p.dbg_acc != nullptr) {
-      int32_t* d = p.dbg_acc + ((size_t) item * kTileM + row) * p.n_mma;
-#pragma unroll
-      for (int i = 0; i < 16; i++) d[c0 + i] = v[i];
-      if (c0 == 0) d[p.n_tile] = rowsum;
-    }
+    if (p.dbg_acc != nullptr) dump_acc(p, item, j, row, c0, v, rowsum);
+    const int32_t corr = -p.kzp * rowsum;
     uint32_t w[4];
-    const int4* b4 = reinterpret_cast<const int4*>(bias + c0);
 #pragma unroll
-    for (int q = 0; q < 4; q++) w[q] = requant4<RQ>(v + 4 * q, p, __ldg(b4 + q), corr);
+    for (int t = 0; t < 4; t++) w[t] = requant4<RQ>(v + 4 * t, p, b[t], corr);
+
     const int valid = n_valid - c0;
-    if (valid <= 0) continue;
-    if (bulk) {
-      // staging pitch = goc (dense image of the output tile); goc % 4 == 0 guaranteed by the host
-      if (valid >= 16 && (p.goc & 15) == 0) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + c0), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                     "r"(w[3])
-                     : "memory");
-      } else {
+    if (valid > 0) {
+      if (bulk) {
+        // staging = dense image of the item's output rows (pitch goc; goc % 4 == 0 guaranteed by the host)
+        const uint32_t s = staging + (uint32_t) (j * kTileM + row) * p.goc + c0;
+        if (valid >= 16 && (p.goc & 15) == 0) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (4 * q < valid) asm volatile("st.shared.b32 [%0], %1;" ::"r"(srow + c0 + 4 * q), "r"(w[q]) : "memory");
+          for (int t = 0; t < 4; t++)
+            if (4 * t < valid) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 4 * t), "r"(w[t]) : "memory");
+        }
+      } else {
+        const long long m = it.m0 + (long long) j * kTileM + row;
+        if (m < p.M) {
+          uint8_t* dst = obase + (size_t) m * p.out_stride + c0;
+          if (valid >= 16 && p.out_vec == 16) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+          } else {
+            store_row_partial(dst, w[0], w[1], w[2], w[3], valid < 16 ? valid : 16, p.out_vec);
+          }
+        }
       }
-    } else if (m < p.M) {
-      store_row16(orow + c0, w, valid < 16 ? valid : 16, p.out_vec);
+    }
+    c += 2;
+    while (c >= ch) {
+      c -= ch;
+      ++j;
     }
   }
 }
@@ -261,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
   const int warp = tid >> 5;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_smem = smem_base + p.smem_b_off;
+  const uint32_t bias_smem = smem_base + p.smem_bias_off;
   const uint32_t a_smem = smem_base + p.smem_a_off;
 
   if (tid == 0) {
@@ -270,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
-      mbar_init(smem_u32(&ctl.tmem_empty[s]), 128);
+      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiPairThreads);
     }
     mbar_init(smem_u32(&ctl.b_full), kLoadThreads);
     fence_mbar_init();
@@ -286,9 +320,10 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
   if (warp >= kLoadWarp0) {
     // ===================================== loaders =====================================
     const int ltid = tid - kLoadWarp0 * 32;
-    if (p.b_resident) {
-      const int bytes = p.groups * p.n_tiles * p.nkc * p.n_mma * 16;
-      copy_bytes16(b_smem, p.wpack, bytes, ltid);
+    {
+      // one-time: folded biases (always) and the packed weights (when they fit) become smem-resident
+      copy_bytes16(bias_smem, reinterpret_cast<const uint8_t*>(p.bias), p.bias_count * 4, ltid);
+      if (p.b_resident) copy_bytes16(b_smem, p.wpack, p.groups * p.n_tiles * p.nkc * p.n_mma * 16, ltid);
       cp_async_mbar_arrive_noinc(smem_u32(&ctl.b_full));
     }
     int stage = 0;
@@ -308,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
           cs = cs < p.skc ? cs : p.skc;
           const uint8_t* wsrc =
               p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.nkc + (size_t) ks * p.skc) * p.n_mma * 16;
-          copy_bytes16(a_stage + p.skc * kChunkBytes, wsrc, cs * p.n_mma * 16, ltid);
+          copy_bytes16(a_stage + p.mt * p.skc * kChunkBytes, wsrc, cs * p.n_mma * 16, ltid);
         }
         fence_proxy_async_smem();  // st.shared fills (padding taps / byte path) -> UMMA reads
         cp_async_mbar_arrive_noinc(smem_u32(&ctl.full[stage]));
@@ -324,6 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     if ((tid & 31) == 0) {
       const uint32_t idesc = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, false);
       const uint32_t b_lbo = (uint32_t) p.n_mma * 16;
+      const uint32_t sub_bytes = (uint32_t) p.skc * kChunkBytes;
       if (p.b_resident) {
         mbar_wait(smem_u32(&ctl.b_full), 0);
         fence_proxy_async_smem();
@@ -346,11 +382,13 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
           cs = cs < p.skc ? cs : p.skc;
           const uint32_t b_base = p.b_resident
               ? b_smem + (uint32_t) (((it.g * p.n_tiles + it.nt) * p.nkc + ks * p.skc) * p.n_mma * 16)
-              : a_stage + p.skc * kChunkBytes;
-          for (int j = 0; j < cs; j += 2) {
-            const uint64_t a_desc = umma_desc_kmajor_noswizzle(a_stage + j * kChunkBytes, kChunkBytes, 128);
-            const uint64_t b_desc = umma_desc_kmajor_noswizzle(b_base + j * b_lbo, b_lbo, 128);
-            umma_i8(d_tmem, a_desc, b_desc, idesc, (ks | j) != 0 ? 1u : 0u);
+              : a_stage + p.mt * sub_bytes;
+          for (int j = 0; j < it.mt_eff; j++) {
+            for (int c = 0; c < cs; c += 2) {
+              const uint64_t a_desc = umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128);
+              const uint64_t b_desc = umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128);
+              umma_i8(d_tmem + j * p.n_mma, a_desc, b_desc, idesc, (ks | c) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(&ctl.empty[stage]));
           if (++stage == p.num_stages) {
@@ -363,42 +401,47 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     }
   } else {
     // ===================================== epilogue =====================================
-    const int grp = warp >> 2;            // 0 or 1
-    const int grp_tid = tid & 127;
-    const uint32_t staging = smem_base + p.smem_stage_off + grp * (kTileM * p.goc);
-    long long li = grp;
+    const int pair = warp >> 3;          // 0 or 1 == TMEM stage
+    const int pw = warp & 7;
+    const int q = pw & 3, half = pw >> 2;
+    const int lane = tid & 31;
+    const int pair_tid = tid & (kEpiPairThreads - 1);
+    const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
+    mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem
+    long long li = pair;
     bool bulk_pending = false;
-    for (long long item = first + grp * step; item < p.total_items; item += 2 * step, li += 2) {
+    for (long long item = first + pair * step; item < p.total_items; item += 2 * step, li += 2) {
       const Item it = decode_item(p, item);
-      const bool bulk = p.out_mode == 1 && (it.m0 + kTileM <= p.M);
+      const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
       if (p.out_mode == 1) {
-        // the previous bulk store of this group must have finished reading the staging buffer
-        if (grp_tid == 0 && bulk_pending) bulk_wait_read<0>();
-        named_bar_sync(1 + grp, 128);
+        // the previous bulk store of this pair must have finished reading the staging buffer
+        if (pair_tid == 0 && bulk_pending) bulk_wait_read<0>();
+        named_bar_sync(1 + pair, kEpiPairThreads);
       }
-      mbar_wait(smem_u32(&ctl.tmem_full[grp]), (uint32_t) ((li >> 1) & 1));
+      mbar_wait(smem_u32(&ctl.tmem_full[pair]), (uint32_t) ((li >> 1) & 1));
       tc_fence_after_sync();
-      const uint32_t tmem_acc = tmem_base + grp * kMaxNMma;
+      const uint32_t tmem_acc = tmem_base + pair * kMaxNMma;
       switch (p.rq_mode) {
-        case 0: epilogue_item<0>(p, it, item, tmem_acc, grp_tid, staging, bulk); break;
-        case 1: epilogue_item<1>(p, it, item, tmem_acc, grp_tid, staging, bulk); break;
-        case 2: epilogue_item<2>(p, it, item, tmem_acc, grp_tid, staging, bulk); break;
-        default: epilogue_item<3>(p, it, item, tmem_acc, grp_tid, staging, bulk); break;
+        case 0: epilogue_item<0>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
+        case 1: epilogue_item<1>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
+        case 2: epilogue_item<2>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
+        case 4: epilogue_item<4>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
+        default: epilogue_item<3>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
       }
-      // accumulator stage may be overwritten by the next-but-one work item
+      // the accumulator stage may be overwritten by the next-but-one work item
       tc_fence_before_sync();
-      mbar_arrive(smem_u32(&ctl.tmem_empty[grp]));
+      mbar_arrive(smem_u32(&ctl.tmem_empty[pair]));
       if (p.out_mode == 1) {
         fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 128);
-        if (bulk && grp_tid == 0) {
-          bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, (uint32_t) (kTileM * p.goc));
+        named_bar_sync(1 + pair, kEpiPairThreads);
+        if (bulk && pair_tid == 0) {
+          bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, (uint32_t) (it.mt_eff * kTileM * p.goc));
           bulk_commit();
           bulk_pending = true;
         }
       }
     }
-    if (grp_tid == 0 && bulk_pending) bulk_wait<0>();
+    if (pair_tid == 0 && bulk_pending) bulk_wait<0>();
   }
 
   tc_fence_before_sync();

@@ -6,12 +6,13 @@
 
 namespace q8 {
 
-constexpr int kTileM = 128;            // rows (output pixels) per work item = UMMA M
-constexpr int kChunkBytes = kTileM * 16;  // one 16-byte K-chunk of an A tile: [128 rows][16 B]
+constexpr int kTileM = 128;               // rows (output pixels) per UMMA = TMEM lanes
+constexpr int kChunkBytes = kTileM * 16;  // one 16-byte K-chunk of an A sub-tile: [128 rows][16 B]
 constexpr int kMaxStages = 16;
-constexpr int kMaxNMma = 256;          // UMMA N limit; also the TMEM column stride of an accumulator stage
-constexpr int kOnesCols = 16;          // extra B rows: row 0 of the block is all-ones -> per-row sum of A
+constexpr int kMaxNMma = 256;             // UMMA N limit; also the TMEM column budget of one accumulator stage
+constexpr int kOnesCols = 16;             // extra B rows: row 0 of the block is all-ones -> per-row sum of A
 constexpr int kMaxNTile = kMaxNMma - kOnesCols;
+constexpr int kMaxSubTiles = 8;           // 128-row sub-tiles per work item (they share one TMEM stage)
 
 enum IgemmMode : int { kModeGemm = 0, kModeConv = 1 };
 
@@ -20,11 +21,12 @@ struct IgemmParams {
   uint8_t* out;
   const uint8_t* wpack;  // [group][n_tile] blocks, each [nkc][n_mma][16 B]  (K-major, no-swizzle core matrices)
   const int32_t* bias;   // [group][n_tiles * n_tile] folded bias (reference pack.h:24,43,63,84)
-  int32_t* dbg_acc;      // optional: raw accumulators [item][128][n_mma]
+  int32_t* dbg_acc;      // optional: raw accumulators [item][sub-tile][128][n_mma]
 
   long long M;           // rows per group = batch * out_h * out_w
-  long long m_tiles;
-  long long total_items; // groups * m_tiles * n_tiles
+  long long m_tiles;     // ceil(M / 128)
+  long long m_super;     // ceil(m_tiles / mt)
+  long long total_items; // groups * m_super * n_tiles
   long long in_stride, out_stride;
   int groups, gic, goc;
 
@@ -34,19 +36,21 @@ struct IgemmParams {
   // tiling
   int K;          // kh*kw*gic
   int nkc;        // 16-byte K chunks incl. padding, even
-  int nkc_real;   // ceil(K/16)
   int skc;        // chunks per pipeline stage, even
   int k_stages;   // ceil(nkc / skc)
+  int mt;         // 128-row sub-tiles per work item
   int n_tiles, n_tile, n_mma;
+  int has_corr;   // 1: B carries the ones block and the epilogue applies  - kzp * rowsum
   int b_resident; // 1: all packed weights live in smem for the whole kernel
   int num_stages; // A(+B) ring depth
   int stage_bytes;
-  int out_mode;   // 0: per-row stores from registers; 1: whole-tile bulk store via smem staging
+  int bias_count; // ints in `bias`
+  int out_mode;   // 0: per-row stores from registers; 1: whole-item bulk store via smem staging
   int out_vec;    // direct stores: widest power-of-two (<=16) dividing base address, out_stride and column offsets
-  int rq_mode;    // 0: fused, shift>=1, no clamp needed; 1: fused, shift>=1, clamp; 2: shift==0; 3: exact slow form
+  int rq_mode;    // 0: fused shift>=2, no clamp; 1: fused shift>=2 + clamp; 2: shift==0; 3: exact slow; 4: fused shift==1
 
   // smem carve-up (byte offsets into dynamic smem, 1024-aligned base)
-  int smem_b_off, smem_a_off, smem_stage_off, smem_total;
+  int smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, staging_bytes, smem_total;
 
   int izp, kzp;
   Q8Requant rq;

@@ -153,9 +153,9 @@ struct qnnp_operator {
   size_t bias_count = 0;
 
   // igemm tiling
-  int K = 0, nkc = 0, nkc_real = 0, skc = 0, k_stages = 0, n_tiles = 0, n_tile = 0, n_mma = 0;
+  int K = 0, nkc = 0, skc = 0, k_stages = 0, mt = 1, n_tiles = 0, n_tile = 0, n_mma = 0, has_corr = 1;
   int b_resident = 0, num_stages = 0, stage_bytes = 0;
-  int smem_b_off = 0, smem_a_off = 0, smem_stage_off = 0, smem_total = 0;
+  int smem_b_off = 0, smem_bias_off = 0, smem_a_off = 0, smem_stage_off = 0, staging_bytes = 0, smem_total = 0;
   bool bulk_capable = false;
   int c_pad = 0;  // dw
 
@@ -182,11 +182,7 @@ void free_operator(qnnp_operator* op) {
   delete op;
 }
 
-int select_rq_mode(const Q8Requant& rq) {
-  if (!rq.fused) return 3;
-  if (rq.shift == 0) return 2;
-  return (rq.qmin == 0 && rq.qmax == 255) ? 0 : 1;
-}
+int select_rq_mode(const Q8Requant& rq) { return q8_requant_mode(rq); }
 
 bool scale_ok(float s) { return s > 0.0f && isnormal(s); }
 
@@ -208,6 +204,80 @@ int32_t fold_bias(int32_t b, size_t k_total, uint8_t izp, uint8_t kzp, const uin
 // ------------------------------------------------------------------------------------------------
 constexpr int kCtlReserve = 2048;  // static SmemCtl + 1024-byte alignment slack
 
+// Tiling + shared-memory plan of the tensor-core kernel; pure function of the operator shape (testable on a CPU box).
+struct IgemmPlan {
+  int K, nkc, skc, k_stages, mt, n_tiles, n_tile, n_mma, has_corr;
+  int b_resident, num_stages, stage_bytes, staging_bytes, bias_bytes;
+  int smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, smem_total;
+  int bulk_capable;
+  size_t w_total, bias_count;
+};
+
+bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, IgemmPlan* pl) {
+  memset(pl, 0, sizeof(*pl));
+  pl->K = (int) K;
+  pl->nkc = (int) round_up(ceil_div(K, 16), 2);
+  const int n_pad = (int) round_up(goc, 16);
+  if (n_pad <= q8::kMaxNTile) {
+    pl->n_tiles = 1;
+    pl->n_tile = n_pad;
+  } else {
+    pl->n_tiles = (int) ceil_div(n_pad, q8::kMaxNTile);
+    pl->n_tile = (int) round_up(ceil_div(n_pad, pl->n_tiles), 16);
+  }
+  pl->has_corr = 1;
+  pl->n_mma = pl->n_tile + q8::kOnesCols;
+  pl->bulk_capable = (groups == 1 && pl->n_tiles == 1 && (goc % 4) == 0) ? 1 : 0;
+  pl->w_total = (size_t) groups * pl->n_tiles * pl->nkc * pl->n_mma * 16;
+  pl->bias_count = (size_t) groups * pl->n_tiles * pl->n_tile;
+  pl->bias_bytes = (int) round_up(pl->bias_count * 4, 128);
+
+  // Preference: as many 128-row sub-tiles per work item as TMEM allows (amortises per-item synchronisation),
+  // subject to >= 3 ring stages and >= 64 KB of loads in flight (or the whole K of 3 items); weights stay
+  // resident in smem when they fit beside that.
+  const int smem_max = smem_optin - kCtlReserve - 1024;
+  int mt_max = q8::kMaxNMma / pl->n_mma;
+  if (mt_max > q8::kMaxSubTiles) mt_max = q8::kMaxSubTiles;
+  if (mt_max < 1) mt_max = 1;
+  if (const char* e = getenv("QNNP_CUDA_MAX_SUBTILES")) {
+    const int v = atoi(e);
+    if (v >= 1 && v < mt_max) mt_max = v;
+  }
+  struct Cand { int mt, skc, resident, stages, stage_bytes, staging; long long inflight; bool ok; };
+  Cand best{0, 0, 0, 0, 0, 0, -1, false};
+  for (int mt = mt_max; mt >= 1 && !best.ok; mt--) {
+    const int staging = pl->bulk_capable ? mt * q8::kTileM * (int) goc : 0;  // per epilogue pair
+    for (int skc = pl->nkc < 8 ? pl->nkc : 8; skc >= 2; skc = (skc > 4 ? 4 : skc - 2)) {
+      const int a_stage = mt * skc * q8::kChunkBytes;
+      const long long fixed = pl->bias_bytes + 2LL * staging;
+      const int resident = ((long long) pl->w_total + fixed + 3LL * a_stage <= smem_max) ? 1 : 0;
+      const int stage_bytes = a_stage + (resident ? 0 : skc * pl->n_mma * 16);
+      const long long room = smem_max - fixed - (resident ? (long long) pl->w_total : 0);
+      int stages = room > 0 ? (int) (room / stage_bytes) : 0;
+      if (stages > q8::kMaxStages) stages = q8::kMaxStages;
+      if (stages < 2) continue;
+      const long long inflight = (long long) stages * a_stage;
+      const bool ok = stages >= 3 && (inflight >= 64 * 1024 || (long long) stages * skc >= pl->nkc * 3LL);
+      if (ok || inflight > best.inflight) best = Cand{mt, skc, resident, stages, stage_bytes, staging, inflight, ok};
+      if (ok) break;
+    }
+  }
+  if (best.mt == 0) return false;
+  pl->mt = best.mt;
+  pl->skc = best.skc;
+  pl->k_stages = (int) ceil_div(pl->nkc, pl->skc);
+  pl->b_resident = best.resident;
+  pl->num_stages = best.stages;
+  pl->stage_bytes = best.stage_bytes;
+  pl->staging_bytes = best.staging;
+  pl->smem_b_off = 0;
+  pl->smem_bias_off = (int) round_up(pl->b_resident ? pl->w_total : 0, 128);
+  pl->smem_a_off = pl->smem_bias_off + pl->bias_bytes;
+  pl->smem_stage_off = pl->smem_a_off + pl->num_stages * pl->stage_bytes;
+  pl->smem_total = pl->smem_stage_off + 2 * pl->staging_bytes + 1024;
+  return true;
+}
+
 enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
   const size_t ks = (size_t) op->kh * op->kw;
   const size_t K = ks * op->gic;
@@ -215,44 +285,21 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
     log_error("convolution too large for the tensor-core path (K=%zu, N=%zu)", K, op->goc);
     return qnnp_status_unsupported_parameter;
   }
-  op->K = (int) K;
-  op->nkc_real = (int) ceil_div(K, 16);
-  op->nkc = (int) round_up(op->nkc_real, 2);
-  const int n_pad = (int) round_up(op->goc, 16);
-  if (n_pad <= q8::kMaxNTile) {
-    op->n_tiles = 1;
-    op->n_tile = n_pad;
-  } else {
-    op->n_tiles = (int) ceil_div(n_pad, q8::kMaxNTile);
-    op->n_tile = (int) round_up(ceil_div(n_pad, op->n_tiles), 16);
-  }
-  op->n_mma = op->n_tile + q8::kOnesCols;
-  op->skc = op->nkc < 8 ? op->nkc : 8;
-  op->k_stages = (int) ceil_div(op->nkc, op->skc);
-
-  const int smem_max = g_lib.max_smem_optin - kCtlReserve;
-  op->bulk_capable = op->groups == 1 && op->n_tiles == 1 && (op->goc % 4) == 0;
-  const int staging = op->bulk_capable ? 2 * q8::kTileM * (int) op->goc : 0;
-  const size_t w_total = (size_t) op->groups * op->n_tiles * op->nkc * op->n_mma * 16;
-  const int a_stage = op->skc * q8::kChunkBytes;
-  op->b_resident = (w_total + (size_t) staging + 3u * (size_t) a_stage <= (size_t) smem_max) ? 1 : 0;
-  op->stage_bytes = a_stage + (op->b_resident ? 0 : op->skc * op->n_mma * 16);
-  const int b_bytes = op->b_resident ? (int) w_total : 0;
-  int stages = (smem_max - b_bytes - staging) / op->stage_bytes;
-  if (stages > q8::kMaxStages) stages = q8::kMaxStages;
-  if (stages < 2) {
-    log_error("shared-memory plan failed (stage %d B, staging %d B)", op->stage_bytes, staging);
+  IgemmPlan pl;
+  if (!plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, &pl)) {
+    log_error("shared-memory plan failed (K=%zu, N=%zu)", K, op->goc);
     return qnnp_status_unsupported_parameter;
   }
-  op->num_stages = stages;
-  op->smem_b_off = 0;
-  op->smem_a_off = (int) round_up(b_bytes, 128);
-  op->smem_stage_off = op->smem_a_off + stages * op->stage_bytes;
-  op->smem_total = op->smem_stage_off + staging + 1024;
+  op->K = pl.K, op->nkc = pl.nkc, op->skc = pl.skc, op->k_stages = pl.k_stages, op->mt = pl.mt;
+  op->n_tiles = pl.n_tiles, op->n_tile = pl.n_tile, op->n_mma = pl.n_mma, op->has_corr = pl.has_corr;
+  op->b_resident = pl.b_resident, op->num_stages = pl.num_stages, op->stage_bytes = pl.stage_bytes;
+  op->staging_bytes = pl.staging_bytes, op->bulk_capable = pl.bulk_capable != 0;
+  op->smem_b_off = pl.smem_b_off, op->smem_bias_off = pl.smem_bias_off, op->smem_a_off = pl.smem_a_off;
+  op->smem_stage_off = pl.smem_stage_off, op->smem_total = pl.smem_total;
+  const size_t w_total = pl.w_total, bias_count = pl.bias_count;
 
   // ---- pack: [group][n_tile][k-chunk][row][16 B]; row n_tile of every block is the all-ones row ----
   std::vector<uint8_t> blob(w_total, 0);
-  const size_t bias_count = (size_t) op->groups * op->n_tiles * op->n_tile;
   std::vector<int32_t> fbias(bias_count, 0);
   for (uint32_t g = 0; g < op->groups; g++) {
     for (int nt = 0; nt < op->n_tiles; nt++) {
@@ -324,18 +371,20 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.dbg_acc = g_lib.dbg_acc;
       p.M = (long long) M;
       p.m_tiles = (long long) ceil_div(M, q8::kTileM);
-      p.total_items = (long long) op->groups * p.m_tiles * op->n_tiles;
+      p.m_super = (long long) ceil_div((size_t) p.m_tiles, (size_t) op->mt);
+      p.total_items = (long long) op->groups * p.m_super * op->n_tiles;
       p.in_stride = (long long) op->in_stride;
       p.out_stride = (long long) op->out_stride;
       p.groups = (int) op->groups, p.gic = (int) op->gic, p.goc = (int) op->goc;
       p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
       p.kh = (int) op->kh, p.kw = (int) op->kw, p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w;
       p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w, p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
-      p.K = op->K, p.nkc = op->nkc, p.nkc_real = op->nkc_real, p.skc = op->skc, p.k_stages = op->k_stages;
-      p.n_tiles = op->n_tiles, p.n_tile = op->n_tile, p.n_mma = op->n_mma;
+      p.K = op->K, p.nkc = op->nkc, p.skc = op->skc, p.k_stages = op->k_stages, p.mt = op->mt;
+      p.n_tiles = op->n_tiles, p.n_tile = op->n_tile, p.n_mma = op->n_mma, p.has_corr = op->has_corr;
       p.b_resident = op->b_resident, p.num_stages = op->num_stages, p.stage_bytes = op->stage_bytes;
-      p.smem_b_off = op->smem_b_off, p.smem_a_off = op->smem_a_off, p.smem_stage_off = op->smem_stage_off;
-      p.smem_total = op->smem_total;
+      p.bias_count = (int) op->bias_count;
+      p.smem_b_off = op->smem_b_off, p.smem_bias_off = op->smem_bias_off, p.smem_a_off = op->smem_a_off;
+      p.smem_stage_off = op->smem_stage_off, p.staging_bytes = op->staging_bytes, p.smem_total = op->smem_total;
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
       p.rq_mode = op->rq_mode;
@@ -678,6 +727,16 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_bias(qnnp_operator_t op, 
   return qnnp_status_success;
 }
 QNNP_EXPORT unsigned long long qnnp_cuda_launch_count(void) { return g_lib.launches.load(); }
+QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int out[20]) {
+  IgemmPlan pl;
+  const int optin = g_lib.initialized ? g_lib.max_smem_optin : 232448;  // B200: 227 KB opt-in
+  if (!plan_igemm(k, n, groups, optin, &pl)) return 0;
+  const int v[20] = {pl.K, pl.nkc, pl.skc, pl.k_stages, pl.mt, pl.n_tiles, pl.n_tile, pl.n_mma, pl.has_corr, pl.b_resident,
+                     pl.num_stages, pl.stage_bytes, pl.staging_bytes, pl.bias_bytes, pl.smem_b_off, pl.smem_bias_off,
+                     pl.smem_a_off, pl.smem_stage_off, pl.smem_total, pl.bulk_capable};
+  for (int i = 0; i < 20; i++) out[i] = v[i];
+  return 1;
+}
 QNNP_EXPORT void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer) { g_lib.dbg_acc = device_buffer; }
 QNNP_EXPORT const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op) {
   if (op == nullptr) return "null";

@@ -81,13 +81,27 @@ Q8_HD int32_t q8_requant_exact_slow(int32_t n, const Q8Requant& p) {
   return y + p.zero_point;
 }
 
-// Fused form for shift >= 1, WITHOUT the final clamp: returns y + zero_point as int32 (may lie
-// outside [0,255]; cannot overflow because the high word of the 64-bit sum fits in int32).
-Q8_HD int32_t q8_requant_fused_unclamped(int32_t n, int32_t multiplier, int64_t c_pos, int64_t c_neg, int32_t shift_m1) {
-  const int64_t c = n < 0 ? c_neg : c_pos;
+// Fused form for shift >= 2, WITHOUT the final clamp: returns y + zero_point as int32 (may lie outside
+// [0,255]; cannot overflow because the high word of the 64-bit sum fits in int32).
+// The sign-dependent addend is built without a predicate: c_neg = c_pos - 2^31 and, for s >= 2, the low
+// word of c_pos is exactly 0x40000000 (bit 31 clear), so
+//     addend = { hi: c_pos_hi + (n >> 31),  lo: c_pos_lo | (n & 0x80000000) }
+// i.e. one logic op and one add instead of compare + two selects.
+Q8_HD int32_t q8_requant_fused_unclamped(int32_t n, int32_t multiplier, int64_t c_pos, int32_t shift_m1) {
+  const uint32_t lo = (uint32_t) c_pos | ((uint32_t) n & 0x80000000u);
+  const int32_t hi = (int32_t) (c_pos >> 32) + (n >> 31);
+  const int64_t c = (int64_t) (((uint64_t) (uint32_t) hi << 32) | lo);
   const int64_t p = (int64_t) n * (int64_t) multiplier + c;
   // (p >> (32 + (s-1))): only the high word matters
   return ((int32_t) (p >> 32)) >> shift_m1;
+}
+
+// shift == 1: here it is c_neg whose low word is 0x40000000, so 2^31 is ADDED for n >= 0 instead.
+Q8_HD int32_t q8_requant_fused_shift1_unclamped(int32_t n, int32_t multiplier, int64_t c_neg) {
+  const uint32_t lo = (uint32_t) c_neg | (~(uint32_t) n & 0x80000000u);
+  const int64_t c = (int64_t) (((uint64_t) (c_neg >> 32) << 32) | lo);
+  const int64_t p = (int64_t) n * (int64_t) multiplier + c;
+  return (int32_t) (p >> 32);
 }
 
 // shift == 0 (scale in [0.5, 1)): the second rounding is the identity, and y + zp could exceed
@@ -101,10 +115,20 @@ Q8_HD int32_t q8_requant_shift0(int32_t n, int32_t multiplier, int32_t zero_poin
   return y < qmin ? qmin : y;
 }
 
+// 0: fused shift in [2,23], clamp provided by the u8 saturating pack; 1: same + explicit clamp;
+// 2: shift == 0; 3: exact slow form (shift > 23); 4: fused shift == 1
+Q8_HD int q8_requant_mode(const Q8Requant& p) {
+  if (!p.fused) return 3;
+  if (p.shift == 0) return 2;
+  if (p.shift == 1) return 4;
+  return (p.qmin == 0 && p.qmax == 255) ? 0 : 1;
+}
+
 Q8_HD int32_t q8_requant(int32_t n, const Q8Requant& p) {
   if (!p.fused) return q8_requant_exact_slow(n, p);
   if (p.shift == 0) return q8_requant_shift0(n, p.multiplier, p.zero_point, p.qmin, p.qmax);
-  int32_t y = q8_requant_fused_unclamped(n, p.multiplier, p.c_pos, p.c_neg, p.shift - 1);
+  int32_t y = p.shift == 1 ? q8_requant_fused_shift1_unclamped(n, p.multiplier, p.c_neg)
+                           : q8_requant_fused_unclamped(n, p.multiplier, p.c_pos, p.shift - 1);
   y = y < p.qmin ? p.qmin : y;
   y = y > p.qmax ? p.qmax : y;
   return y;
