@@ -49,10 +49,12 @@ enum qnnp_status qnnp_cuda_requantize_q31(
 void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer);
 
 /* The tiling / shared-memory plan the tensor-core kernel would use for a K x N (x groups) operator; needs no GPU.
+ * folded != 0: plan for the mode in which bias and zero-point correction run as extra UMMAs (bias_steps of them).
  * out = {K, nkc, skc, k_stages, mt, n_tiles, n_tile, n_mma, has_corr, b_resident, num_stages, stage_bytes,
- *        staging_bytes, bias_bytes, smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, smem_total, bulk_capable}.
- * Returns 1 on success, 0 if no plan fits. */
-int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int out[20]);
+ *        staging_bytes, bias_bytes, smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, smem_total, bulk_capable,
+ *        folded, bias_steps, blk_chunks, good}.  Returns 1 on success, 0 if no plan fits. */
+int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int folded, int bias_steps, int out[24]);
+int qnnp_cuda_debug_operator_is_folded(qnnp_operator_t op);
 
 /* Name of the kernel family an operator was routed to: "igemm-gemm", "igemm-conv", "dwconv3x3", "direct". */
 const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op);

@@ -172,30 +172,30 @@ __device__ __forceinline__ void copy_bytes16(uint32_t dst, const uint8_t* src, i
 // ------------------------------------------------------------------------------------------------
 // epilogue
 // ------------------------------------------------------------------------------------------------
+// Requantise one accumulator (requant_math.h has the derivation and the host-checked reference forms).
+// RQ 0/1: fused form, shift in [2,23]:  y = hi32(n*mult + {c_hi, c_lo | sign(n)}) + (n >> 31)  >> (shift-1)
+//         = LOP3 + IMAD.HI + LEA.HI + SHF per value (+ 1/2 I2IP for the saturating pack).
 template <int RQ>
-__device__ __forceinline__ uint32_t requant4(const int32_t* v, const IgemmParams& p, const int4 b, int32_t corr) {
-  int32_t y[4];
-  const int32_t bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int32_t n = v[i] + bb[i] + corr;
-    if constexpr (RQ == 0) {
-      y[i] = q8_requant_fused_unclamped(n, p.rq.multiplier, p.rq.c_pos, p.rq.shift - 1);
-    } else if constexpr (RQ == 1) {
-      int32_t t = q8_requant_fused_unclamped(n, p.rq.multiplier, p.rq.c_pos, p.rq.shift - 1);
-      t = max(t, p.rq.qmin);
-      y[i] = min(t, p.rq.qmax);
-    } else if constexpr (RQ == 2) {
-      y[i] = q8_requant_shift0(n, p.rq.multiplier, p.rq.zero_point, p.rq.qmin, p.rq.qmax);
-    } else if constexpr (RQ == 4) {
-      int32_t t = q8_requant_fused_shift1_unclamped(n, p.rq.multiplier, p.rq.c_neg);
-      t = max(t, p.rq.qmin);
-      y[i] = min(t, p.rq.qmax);
-    } else {
-      y[i] = q8_requant_exact_slow(n, p.rq);
+__device__ __forceinline__ int32_t requant_dev(int32_t n, const IgemmParams& p) {
+  if constexpr (RQ == 0 || RQ == 1) {
+    const uint32_t lo = (uint32_t) p.rq.c_pos | ((uint32_t) n & 0x80000000u);
+    const int64_t addend = (int64_t) (((uint64_t) (uint32_t) (p.rq.c_pos >> 32) << 32) | lo);
+    const int32_t hi = (int32_t) (((int64_t) n * (int64_t) p.rq.multiplier + addend) >> 32);
+    int32_t y = (hi + (n >> 31)) >> (p.rq.shift - 1);
+    if constexpr (RQ == 1) {
+      y = max(y, p.rq.qmin);
+      y = min(y, p.rq.qmax);
     }
+    return y;
+  } else if constexpr (RQ == 2) {
+    return q8_requant_shift0(n, p.rq.multiplier, p.rq.zero_point, p.rq.qmin, p.rq.qmax);
+  } else if constexpr (RQ == 4) {
+    int32_t y = q8_requant_fused_shift1_unclamped(n, p.rq.multiplier, p.rq.c_neg);
+    y = max(y, p.rq.qmin);
+    return min(y, p.rq.qmax);
+  } else {
+    return q8_requant_exact_slow(n, p.rq);
   }
-  return pack_sat_u8x4(y[0], y[1], y[2], y[3]);  // saturation to [0,255] is the clamp when qmin=0,qmax=255
 }
 
 // Slow path of the direct store: fewer than 16 valid bytes, or a destination that is not 16-byte aligned.
@@ -209,76 +209,120 @@ __device__ __noinline__ void store_row_partial(uint8_t* dst, uint32_t w0, uint32
   for (; i < valid; i++) dst[i] = (uint8_t) (w[i >> 2] >> (8 * (i & 3)));
 }
 
-__device__ __noinline__ void dump_acc(const IgemmParams& p, long long item, int j, int row, int c0, const int32_t* v,
-                                      int32_t rowsum) {
-  int32_t* d = p.dbg_acc + (((size_t) item * p.mt + j) * kTileM + row) * p.n_mma;
-  for (int i = 0; i < 16; i++) d[c0 + i] = v[i];
-  if (c0 == 0 && p.has_corr) d[p.n_tile] = rowsum;
-}
+struct EpiCtx {
+  uint32_t tlane;      // TMEM address of this warp's lane quarter, column 0 of the accumulator stage
+  uint32_t bias_base;  // smem address of this (group, n_tile)'s folded biases ("ones" mode)
+  uint32_t staging;    // smem staging buffer of the epilogue pair (bulk mode)
+  uint8_t* obase;      // out + g*goc + nt*n_tile
+  long long item;
+  int row;             // row inside a sub-tile == TMEM lane
+  int n_valid;         // valid output channels of this n-tile
+  bool bulk;
+};
 
-// One epilogue warp: lane quarter q = warp % 4 of the accumulator, every second (sub-tile, 16-column) unit.
-template <int RQ>
-__device__ __forceinline__ void epilogue_item(
-    const IgemmParams& p, const Item& it, long long item, uint32_t tmem_acc, int q, int half, int lane, uint32_t bias_smem,
-    uint32_t staging, bool bulk) {
-  const int row = q * 32 + lane;  // TMEM lane == row inside a sub-tile
-  const uint32_t tlane = tmem_acc + ((uint32_t) (q * 32) << 16);
-  const int ch = p.n_tile >> 4;   // 16-column chunks per sub-tile
-  const int units = it.mt_eff * ch;
-  const int n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
-  const uint32_t bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
-  uint8_t* const obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
-
-  int j = half / ch, c = half - j * ch;
-  for (int u = half; u < units; u += 2) {
-    const int c0 = c << 4;
-    int32_t v[16];
-    int32_t rowsum = 0;
-    tmem_ld16(tlane + j * p.n_mma + c0, v);
-    if (p.has_corr) tmem_ld1(tlane + j * p.n_mma + p.n_tile, rowsum);
-    int4 b[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(b[t].x), "=r"(b[t].y), "=r"(b[t].z), "=r"(b[t].w)
-                   : "r"(bias_base + (uint32_t) (c0 + 4 * t) * 4));
-    tmem_ld_wait();
-    if (p.dbg_acc != nullptr) dump_acc(p, item, j, row, c0, v, rowsum);
-    const int32_t corr = -p.kzp * rowsum;
-    uint32_t w[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) w[t] = requant4<RQ>(v + 4 * t, p, b[t], corr);
-
-    const int valid = n_valid - c0;
-    if (valid > 0) {
-      if (bulk) {
-        // staging = dense image of the item's output rows (pitch goc; goc % 4 == 0 guaranteed by the host)
-        const uint32_t s = staging + (uint32_t) (j * kTileM + row) * p.goc + c0;
-        if (valid >= 16 && (p.goc & 15) == 0) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                       : "memory");
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; t++)
-            if (4 * t < valid) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 4 * t), "r"(w[t]) : "memory");
-        }
+// 16 output bytes (4 packed words) of row `m`, columns [c0, c0+16) of the n-tile
+__device__ __forceinline__ void emit16(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, uint32_t w0,
+                                       uint32_t w1, uint32_t w2, uint32_t w3) {
+  const int valid = e.n_valid - c0;
+  if (valid <= 0) return;
+  if (e.bulk) {
+    // staging = dense image of the item's output rows (pitch goc; goc % 4 == 0 guaranteed by the host)
+    const uint32_t s = e.staging + (uint32_t) (j * kTileM + e.row) * p.goc + c0;
+    if (valid >= 16 && (p.goc & 15) == 0) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+    } else {
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(s), "r"(w0) : "memory");
+      if (valid > 4) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 4), "r"(w1) : "memory");
+      if (valid > 8) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 8), "r"(w2) : "memory");
+      if (valid > 12) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 12), "r"(w3) : "memory");
+    }
+  } else {
+    const long long m = it.m0 + (long long) j * kTileM + e.row;
+    if (m < p.M) {
+      uint8_t* dst = e.obase + (size_t) m * p.out_stride + c0;
+      if (valid >= 16 && p.out_vec == 16) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
       } else {
-        const long long m = it.m0 + (long long) j * kTileM + row;
-        if (m < p.M) {
-          uint8_t* dst = obase + (size_t) m * p.out_stride + c0;
-          if (valid >= 16 && p.out_vec == 16) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-          } else {
-            store_row_partial(dst, w[0], w[1], w[2], w[3], valid < 16 ? valid : 16, p.out_vec);
-          }
-        }
+        store_row_partial(dst, w0, w1, w2, w3, valid < 16 ? valid : 16, p.out_vec);
       }
     }
+  }
+}
+
+// W (16 or 32) accumulator columns of one row: TMEM -> registers -> requantise -> pack -> store.
+// FOLDED: the accumulator already contains bias and zero-point correction (extra UMMAs); otherwise
+// ("ones" mode) the folded bias comes from smem and -kzp*rowsum from accumulator column n_tile.
+template <int RQ, int W, bool FOLDED>
+__device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0) {
+  int32_t v[W];
+  const uint32_t taddr = e.tlane + j * p.n_mma + c0;
+  if constexpr (W == 32) {
+    tmem_ld32(taddr, v);
+  } else {
+    tmem_ld16(taddr, v);
+  }
+  int32_t rowsum = 0;
+  if constexpr (!FOLDED) {
+    if (p.has_corr) tmem_ld1(e.tlane + j * p.n_mma + p.n_tile, rowsum);
+  }
+  tmem_ld_wait();
+  if (p.dbg_acc != nullptr) {  // bring-up aid; v[] is only indexed with constants, so it stays in registers
+    int32_t* d = p.dbg_acc + (((size_t) e.item * p.mt + j) * kTileM + e.row) * p.n_mma;
+#pragma unroll
+    for (int i = 0; i < W; i++) d[c0 + i] = v[i];
+    if (!FOLDED && c0 == 0 && p.has_corr) d[p.n_tile] = rowsum;
+  }
+  if constexpr (!FOLDED) {
+    const int32_t corr = -p.kzp * rowsum;
+#pragma unroll
+    for (int t = 0; t < W / 4; t++) {
+      int4 b;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                   : "r"(e.bias_base + (uint32_t) (c0 + 4 * t) * 4));
+      v[4 * t + 0] += b.x + corr;
+      v[4 * t + 1] += b.y + corr;
+      v[4 * t + 2] += b.z + corr;
+      v[4 * t + 3] += b.w + corr;
+    }
+  }
+  uint32_t w[W / 4];
+#pragma unroll
+  for (int t = 0; t < W / 4; t++)
+    w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p), requant_dev<RQ>(v[4 * t + 1], p), requant_dev<RQ>(v[4 * t + 2], p),
+                         requant_dev<RQ>(v[4 * t + 3], p));  // saturation to [0,255] is the clamp when qmin=0,qmax=255
+#pragma unroll
+  for (int t = 0; t < W / 16; t++) emit16(p, it, e, j, c0 + 16 * t, w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
+}
+
+// One epilogue warp: lane quarter q of the accumulator, every second (sub-tile, column-block) unit of the item.
+template <int RQ, bool FOLDED>
+__device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
+  constexpr int W = FOLDED ? 32 : 16;
+  const int full = p.n_tile / W;            // full-width units per sub-tile
+  const int per_sub = full + ((p.n_tile % W) ? 1 : 0);
+  const int units = it.mt_eff * per_sub;
+  int j = half / per_sub, c = half - j * per_sub;
+  for (int u = half; u < units; u += 2) {
+    if (c < full) {
+      epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W);
+    } else {
+      epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
+    }
     c += 2;
-    while (c >= ch) {
-      c -= ch;
+    while (c >= per_sub) {
+      c -= per_sub;
       ++j;
     }
+  }
+}
+
+template <int RQ>
+__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
+  if (p.folded) {
+    epilogue_item<RQ, true>(p, it, e, half);
+  } else {
+    epilogue_item<RQ, false>(p, it, e, half);
   }
 }
 
@@ -323,7 +367,15 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     {
       // one-time: folded biases (always) and the packed weights (when they fit) become smem-resident
       copy_bytes16(bias_smem, reinterpret_cast<const uint8_t*>(p.bias), p.bias_count * 4, ltid);
-      if (p.b_resident) copy_bytes16(b_smem, p.wpack, p.groups * p.n_tiles * p.nkc * p.n_mma * 16, ltid);
+      if (p.b_resident) copy_bytes16(b_smem, p.wpack, p.groups * p.n_tiles * p.blk_chunks * p.n_mma * 16, ltid);
+      if (p.folded) {
+        // constant A operand of the bias UMMAs: every row = [255 x 31, 1]  (chunk 0 = k 0..15, chunk 1 = k 16..31)
+        const uint32_t ac = smem_base + p.smem_aconst_off + (uint32_t) ltid * 16;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ac), "r"(0xFFFFFFFFu) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %2};" ::"r"(ac + kChunkBytes), "r"(0xFFFFFFFFu), "r"(0x01FFFFFFu)
+                     : "memory");
+        fence_proxy_async_smem();
+      }
       cp_async_mbar_arrive_noinc(smem_u32(&ctl.b_full));
     }
     int stage = 0;
@@ -342,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
           int cs = p.nkc - ks * p.skc;
           cs = cs < p.skc ? cs : p.skc;
           const uint8_t* wsrc =
-              p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.nkc + (size_t) ks * p.skc) * p.n_mma * 16;
+              p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.blk_chunks + (size_t) ks * p.skc) * p.n_mma * 16;
           copy_bytes16(a_stage + p.mt * p.skc * kChunkBytes, wsrc, cs * p.n_mma * 16, ltid);
         }
         fence_proxy_async_smem();  // st.shared fills (padding taps / byte path) -> UMMA reads
@@ -357,9 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
   } else if (warp == kMmaWarp) {
     // ===================================== UMMA issue =====================================
     if ((tid & 31) == 0) {
-      const uint32_t idesc = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, false);
+      const uint32_t idesc_main = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, p.b_signed != 0);
+      const uint32_t idesc_us = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, true);  // u8 x s8
       const uint32_t b_lbo = (uint32_t) p.n_mma * 16;
       const uint32_t sub_bytes = (uint32_t) p.skc * kChunkBytes;
+      const uint32_t a_const = smem_base + p.smem_aconst_off;
       if (p.b_resident) {
         mbar_wait(smem_u32(&ctl.b_full), 0);
         fence_proxy_async_smem();
@@ -373,6 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
         mbar_wait(smem_u32(&ctl.tmem_empty[as]), (uint32_t) ((li >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * kMaxNMma;
+        // base of this (group, n_tile)'s resident block: [B1: nkc][B2 full: 2][B2 tail: 2][bias digits: 2 per step]
+        const uint32_t blk = b_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.blk_chunks) * b_lbo;
         for (int ks = 0; ks < p.k_stages; ks++) {
           mbar_wait(smem_u32(&ctl.full[stage]), phase);
           fence_proxy_async_smem();
@@ -380,14 +436,28 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
           const uint32_t a_stage = a_smem + stage * p.stage_bytes;
           int cs = p.nkc - ks * p.skc;
           cs = cs < p.skc ? cs : p.skc;
-          const uint32_t b_base = p.b_resident
-              ? b_smem + (uint32_t) (((it.g * p.n_tiles + it.nt) * p.nkc + ks * p.skc) * p.n_mma * 16)
-              : a_stage + p.mt * sub_bytes;
+          const uint32_t b_base = p.b_resident ? blk + (uint32_t) (ks * p.skc) * b_lbo : a_stage + p.mt * sub_bytes;
           for (int j = 0; j < it.mt_eff; j++) {
+            const uint32_t d = d_tmem + j * p.n_mma;
+            uint32_t acc = ks != 0 ? 1u : 0u;
+            if (p.folded && ks == 0) {
+              // accumulator := folded bias  (A = [255 x31, 1] in every row, B = signed base-255 digits)
+              for (int t = 0; t < p.bias_steps; t++) {
+                umma_i8(d, umma_desc_kmajor_noswizzle(a_const, kChunkBytes, 128),
+                        umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo, b_lbo, 128), idesc_us, acc);
+                acc = 1u;
+              }
+            }
             for (int c = 0; c < cs; c += 2) {
               const uint64_t a_desc = umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128);
-              const uint64_t b_desc = umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128);
-              umma_i8(d_tmem + j * p.n_mma, a_desc, b_desc, idesc, (ks | c) != 0 ? 1u : 0u);
+              umma_i8(d, a_desc, umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128), idesc_main, acc);
+              acc = 1u;
+              if (p.has_b2) {
+                // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
+                const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
+                umma_i8(d, a_desc, umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo, b_lbo, 128),
+                        idesc_us, 1u);
+              }
             }
           }
           umma_commit(smem_u32(&ctl.empty[stage]));
@@ -420,13 +490,21 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
       }
       mbar_wait(smem_u32(&ctl.tmem_full[pair]), (uint32_t) ((li >> 1) & 1));
       tc_fence_after_sync();
-      const uint32_t tmem_acc = tmem_base + pair * kMaxNMma;
+      EpiCtx e;
+      e.tlane = tmem_base + pair * kMaxNMma + ((uint32_t) (q * 32) << 16);
+      e.bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
+      e.staging = staging;
+      e.obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
+      e.item = item;
+      e.row = q * 32 + lane;
+      e.n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
+      e.bulk = bulk;
       switch (p.rq_mode) {
-        case 0: epilogue_item<0>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
-        case 1: epilogue_item<1>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
-        case 2: epilogue_item<2>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
-        case 4: epilogue_item<4>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
-        default: epilogue_item<3>(p, it, item, tmem_acc, q, half, lane, bias_smem, staging, bulk); break;
+        case 0: epilogue_dispatch<0>(p, it, e, half); break;
+        case 1: epilogue_dispatch<1>(p, it, e, half); break;
+        case 2: epilogue_dispatch<2>(p, it, e, half); break;
+        case 4: epilogue_dispatch<4>(p, it, e, half); break;
+        default: epilogue_dispatch<3>(p, it, e, half); break;
       }
       // the accumulator stage may be overwritten by the next-but-one work item
       tc_fence_before_sync();

@@ -40,7 +40,15 @@ struct IgemmParams {
   int k_stages;   // ceil(nkc / skc)
   int mt;         // 128-row sub-tiles per work item
   int n_tiles, n_tile, n_mma;
-  int has_corr;   // 1: B carries the ones block and the epilogue applies  - kzp * rowsum
+  int has_corr;   // "ones" mode only: B carries the ones block and the epilogue applies  - kzp * rowsum
+  // "folded" mode: bias and zero-point correction are accumulated by extra UMMAs, the epilogue only requantises
+  int folded;      // 1: folded mode (requires resident weights)
+  int b_signed;    // folded: main B operand is (w - 128) as s8 (kzp != 0); 0: raw u8 weights (kzp == 0)
+  int has_b2;      // folded: second UMMA per K step with the constant (128 - kzp) operand
+  int bias_steps;  // folded: number of K=32 UMMA steps that add the folded bias (A = [255 x31, 1], B = s8 digits)
+  int blk_chunks;  // 16-byte K chunks per (group, n_tile) block of `wpack`: nkc [+ 4 + 2*bias_steps when folded]
+  int k_tail_pad;  // 1 if K < nkc*16 (last chunk pair partly padding -> uses the "tail" constant operand)
+  int smem_aconst_off;
   int b_resident; // 1: all packed weights live in smem for the whole kernel
   int num_stages; // A(+B) ring depth
   int stage_bytes;

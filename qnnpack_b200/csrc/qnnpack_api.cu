@@ -154,6 +154,7 @@ struct qnnp_operator {
 
   // igemm tiling
   int K = 0, nkc = 0, skc = 0, k_stages = 0, mt = 1, n_tiles = 0, n_tile = 0, n_mma = 0, has_corr = 1;
+  int folded = 0, b_signed = 0, has_b2 = 0, bias_steps = 0, blk_chunks = 0, k_tail_pad = 0, smem_aconst_off = 0;
   int b_resident = 0, num_stages = 0, stage_bytes = 0;
   int smem_b_off = 0, smem_bias_off = 0, smem_a_off = 0, smem_stage_off = 0, staging_bytes = 0, smem_total = 0;
   bool bulk_capable = false;
@@ -207,30 +208,41 @@ constexpr int kCtlReserve = 2048;  // static SmemCtl + 1024-byte alignment slack
 // Tiling + shared-memory plan of the tensor-core kernel; pure function of the operator shape (testable on a CPU box).
 struct IgemmPlan {
   int K, nkc, skc, k_stages, mt, n_tiles, n_tile, n_mma, has_corr;
+  int folded, bias_steps, blk_chunks, k_tail_pad;
   int b_resident, num_stages, stage_bytes, staging_bytes, bias_bytes;
-  int smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, smem_total;
+  int smem_b_off, smem_bias_off, smem_aconst_off, smem_a_off, smem_stage_off, smem_total;
   int bulk_capable;
+  int good;  // 1 if the ring meets the in-flight target (>= 3 stages and >= 64 KB or 3 items' worth of K)
   size_t w_total, bias_count;
 };
 
-bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, IgemmPlan* pl) {
+// folded != 0 requests the mode in which bias and zero-point correction are accumulated by extra UMMAs
+// (needs the weights resident in smem; the function reports failure rather than silently changing mode).
+bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folded, int bias_steps, IgemmPlan* pl) {
   memset(pl, 0, sizeof(*pl));
   pl->K = (int) K;
   pl->nkc = (int) round_up(ceil_div(K, 16), 2);
+  pl->k_tail_pad = (K < (size_t) pl->nkc * 16) ? 1 : 0;
+  pl->folded = folded ? 1 : 0;
+  pl->bias_steps = folded ? bias_steps : 0;
+  const int ones = folded ? 0 : q8::kOnesCols;
+  const int n_tile_max = q8::kMaxNMma - ones;
   const int n_pad = (int) round_up(goc, 16);
-  if (n_pad <= q8::kMaxNTile) {
+  if (n_pad <= n_tile_max) {
     pl->n_tiles = 1;
     pl->n_tile = n_pad;
   } else {
-    pl->n_tiles = (int) ceil_div(n_pad, q8::kMaxNTile);
+    pl->n_tiles = (int) ceil_div(n_pad, n_tile_max);
     pl->n_tile = (int) round_up(ceil_div(n_pad, pl->n_tiles), 16);
   }
-  pl->has_corr = 1;
-  pl->n_mma = pl->n_tile + q8::kOnesCols;
+  pl->has_corr = folded ? 0 : 1;
+  pl->n_mma = pl->n_tile + ones;
+  pl->blk_chunks = pl->nkc + (folded ? 4 + 2 * bias_steps : 0);
   pl->bulk_capable = (groups == 1 && pl->n_tiles == 1 && (goc % 4) == 0) ? 1 : 0;
-  pl->w_total = (size_t) groups * pl->n_tiles * pl->nkc * pl->n_mma * 16;
+  pl->w_total = (size_t) groups * pl->n_tiles * pl->blk_chunks * pl->n_mma * 16;
   pl->bias_count = (size_t) groups * pl->n_tiles * pl->n_tile;
   pl->bias_bytes = (int) round_up(pl->bias_count * 4, 128);
+  const int aconst_bytes = folded ? 2 * q8::kChunkBytes : 0;
 
   // Preference: as many 128-row sub-tiles per work item as TMEM allows (amortises per-item synchronisation),
   // subject to >= 3 ring stages and >= 64 KB of loads in flight (or the whole K of 3 items); weights stay
@@ -249,8 +261,9 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, IgemmPlan
     const int staging = pl->bulk_capable ? mt * q8::kTileM * (int) goc : 0;  // per epilogue pair
     for (int skc = pl->nkc < 8 ? pl->nkc : 8; skc >= 2; skc = (skc > 4 ? 4 : skc - 2)) {
       const int a_stage = mt * skc * q8::kChunkBytes;
-      const long long fixed = pl->bias_bytes + 2LL * staging;
+      const long long fixed = pl->bias_bytes + aconst_bytes + 2LL * staging;
       const int resident = ((long long) pl->w_total + fixed + 3LL * a_stage <= smem_max) ? 1 : 0;
+      if (folded && !resident) continue;
       const int stage_bytes = a_stage + (resident ? 0 : skc * pl->n_mma * 16);
       const long long room = smem_max - fixed - (resident ? (long long) pl->w_total : 0);
       int stages = room > 0 ? (int) (room / stage_bytes) : 0;
@@ -263,6 +276,7 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, IgemmPlan
     }
   }
   if (best.mt == 0) return false;
+  pl->good = best.ok ? 1 : 0;
   pl->mt = best.mt;
   pl->skc = best.skc;
   pl->k_stages = (int) ceil_div(pl->nkc, pl->skc);
@@ -272,10 +286,33 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, IgemmPlan
   pl->staging_bytes = best.staging;
   pl->smem_b_off = 0;
   pl->smem_bias_off = (int) round_up(pl->b_resident ? pl->w_total : 0, 128);
-  pl->smem_a_off = pl->smem_bias_off + pl->bias_bytes;
+  pl->smem_aconst_off = pl->smem_bias_off + pl->bias_bytes;
+  pl->smem_a_off = pl->smem_aconst_off + aconst_bytes;
   pl->smem_stage_off = pl->smem_a_off + pl->num_stages * pl->stage_bytes;
   pl->smem_total = pl->smem_stage_off + 2 * pl->staging_bytes + 1024;
   return true;
+}
+
+// Folded-mode bias operand: bias' = 255 * Q + e with e in [-127, 127]; Q is spread over 31 signed digits per
+// UMMA step (|digit| <= 127), so that  sum_k A[k] * digit[k]  with A = [255 x31, 1]  reproduces bias' exactly.
+constexpr int kBiasDigitsPerStep = 31;
+constexpr int kMaxBiasSteps = 4;
+
+void bias_split(int32_t b, int64_t* q_out, int* e_out) {
+  int64_t r = ((int64_t) b % 255 + 255) % 255;  // [0, 254]
+  const int e = r <= 127 ? (int) r : (int) r - 255;
+  *e_out = e;
+  *q_out = ((int64_t) b - e) / 255;
+}
+
+int bias_steps_needed(int32_t b) {
+  int64_t q;
+  int e;
+  bias_split(b, &q, &e);
+  const int64_t aq = q < 0 ? -q : q;
+  const int64_t per_step = (int64_t) kBiasDigitsPerStep * 127;
+  const int64_t steps = (aq + per_step - 1) / per_step;
+  return steps < 1 ? 1 : (steps > 1000000 ? 1000000 : (int) steps);
 }
 
 enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
@@ -285,33 +322,84 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
     log_error("convolution too large for the tensor-core path (K=%zu, N=%zu)", K, op->goc);
     return qnnp_status_unsupported_parameter;
   }
+  // folded biases first: their magnitude decides whether the tensor core can absorb them
+  const size_t oc_all = (size_t) op->groups * op->goc;
+  std::vector<int32_t> fb(oc_all);
+  int steps = 1;
+  for (size_t oc = 0; oc < oc_all; oc++) {
+    fb[oc] = fold_bias(bias[oc], K, op->izp, op->kzp, kernel + oc * K);
+    const int s = bias_steps_needed(fb[oc]);
+    if (s > steps) steps = s;
+  }
+  const char* mode_env = getenv("QNNP_CUDA_IGEMM_MODE");
+  const bool want_folded = !(mode_env != nullptr && strcmp(mode_env, "ones") == 0) && steps <= kMaxBiasSteps;
   IgemmPlan pl;
-  if (!plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, &pl)) {
+  // folded mode only when its plan keeps a healthy ring; otherwise the "ones" plan (weights may stream)
+  bool planned = want_folded && plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, 1, steps, &pl) && pl.good;
+  if (!planned) planned = plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, 0, 0, &pl);
+  if (!planned) {
     log_error("shared-memory plan failed (K=%zu, N=%zu)", K, op->goc);
     return qnnp_status_unsupported_parameter;
   }
   op->K = pl.K, op->nkc = pl.nkc, op->skc = pl.skc, op->k_stages = pl.k_stages, op->mt = pl.mt;
   op->n_tiles = pl.n_tiles, op->n_tile = pl.n_tile, op->n_mma = pl.n_mma, op->has_corr = pl.has_corr;
+  op->folded = pl.folded, op->bias_steps = pl.bias_steps, op->blk_chunks = pl.blk_chunks, op->k_tail_pad = pl.k_tail_pad;
+  op->b_signed = (pl.folded && op->kzp != 0) ? 1 : 0;
+  op->has_b2 = (pl.folded && op->kzp != 0) ? 1 : 0;
   op->b_resident = pl.b_resident, op->num_stages = pl.num_stages, op->stage_bytes = pl.stage_bytes;
   op->staging_bytes = pl.staging_bytes, op->bulk_capable = pl.bulk_capable != 0;
-  op->smem_b_off = pl.smem_b_off, op->smem_bias_off = pl.smem_bias_off, op->smem_a_off = pl.smem_a_off;
-  op->smem_stage_off = pl.smem_stage_off, op->smem_total = pl.smem_total;
+  op->smem_b_off = pl.smem_b_off, op->smem_bias_off = pl.smem_bias_off, op->smem_aconst_off = pl.smem_aconst_off;
+  op->smem_a_off = pl.smem_a_off, op->smem_stage_off = pl.smem_stage_off, op->smem_total = pl.smem_total;
   const size_t w_total = pl.w_total, bias_count = pl.bias_count;
 
-  // ---- pack: [group][n_tile][k-chunk][row][16 B]; row n_tile of every block is the all-ones row ----
+  // ---- pack: per (group, n_tile) block, chunk-major [chunk][row (n_mma)][16 B] -------------------------------
+  //   chunks [0, nkc)            weights, K-major; "ones" mode: raw u8 + all-ones row n_tile;
+  //                              folded mode: (w - 128) as s8 when kzp != 0, raw u8 when kzp == 0
+  //   folded only:
+  //   chunks [nkc, nkc+2)        constant (128 - kzp) operand, all 32 k valid
+  //   chunks [nkc+2, nkc+4)      same, zero where the last chunk pair is K padding
+  //   chunks [nkc+4+2t, +2)      bias digits of step t (k = 0..30: digits of Q, k = 31: e in step 0)
   std::vector<uint8_t> blob(w_total, 0);
   std::vector<int32_t> fbias(bias_count, 0);
+  const uint8_t wflip = op->b_signed ? 0x80 : 0x00;
+  const uint8_t b2val = (uint8_t) (int8_t) (128 - (int) op->kzp);
   for (uint32_t g = 0; g < op->groups; g++) {
     for (int nt = 0; nt < op->n_tiles; nt++) {
-      uint8_t* blk = blob.data() + ((size_t) g * op->n_tiles + nt) * op->nkc * op->n_mma * 16;
+      uint8_t* blk = blob.data() + ((size_t) g * op->n_tiles + nt) * op->blk_chunks * op->n_mma * 16;
+      auto at = [&](size_t chunk, size_t row, size_t byte) -> uint8_t& { return blk[(chunk * op->n_mma + row) * 16 + byte]; };
       for (int r = 0; r < op->n_tile; r++) {
         const size_t oc = (size_t) nt * op->n_tile + r;
         if (oc >= op->goc) break;
         const uint8_t* wrow = kernel + ((size_t) g * op->goc + oc) * K;
-        for (size_t k = 0; k < K; k++) blk[((k >> 4) * op->n_mma + r) * 16 + (k & 15)] = wrow[k];
-        fbias[((size_t) g * op->n_tiles + nt) * op->n_tile + r] = fold_bias(bias[g * op->goc + oc], K, op->izp, op->kzp, wrow);
+        for (size_t k = 0; k < K; k++) at(k >> 4, r, k & 15) = wrow[k] ^ wflip;
+        const int32_t b = fb[(size_t) g * op->goc + oc];
+        fbias[((size_t) g * op->n_tiles + nt) * op->n_tile + r] = b;
+        if (op->folded) {
+          int64_t q;
+          int e;
+          bias_split(b, &q, &e);
+          for (int t = 0; t < op->bias_steps; t++) {
+            for (int k = 0; k < kBiasDigitsPerStep; k++) {
+              const int64_t d = q > 127 ? 127 : (q < -127 ? -127 : q);
+              q -= d;
+              at(op->nkc + 4 + 2 * t + (k >> 4), r, k & 15) = (uint8_t) (int8_t) d;
+            }
+            at(op->nkc + 4 + 2 * t + 1, r, 15) = (uint8_t) (int8_t) (t == 0 ? e : 0);
+          }
+        }
       }
-      for (size_t k = 0; k < K; k++) blk[((k >> 4) * op->n_mma + op->n_tile) * 16 + (k & 15)] = 1;
+      if (op->folded) {
+        if (op->has_b2) {
+          const size_t k_last = (size_t) (op->nkc - 2) * 16;  // first k of the last chunk pair
+          for (int r = 0; r < op->n_tile; r++)
+            for (int k = 0; k < 32; k++) {
+              at(op->nkc + (k >> 4), r, k & 15) = b2val;
+              at(op->nkc + 2 + (k >> 4), r, k & 15) = (k_last + k < K) ? b2val : 0;
+            }
+        }
+      } else {
+        for (size_t k = 0; k < K; k++) at(k >> 4, op->n_tile, k & 15) = 1;
+      }
     }
   }
   op->weights_bytes = w_total;
@@ -381,6 +469,8 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w, p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
       p.K = op->K, p.nkc = op->nkc, p.skc = op->skc, p.k_stages = op->k_stages, p.mt = op->mt;
       p.n_tiles = op->n_tiles, p.n_tile = op->n_tile, p.n_mma = op->n_mma, p.has_corr = op->has_corr;
+      p.folded = op->folded, p.b_signed = op->b_signed, p.has_b2 = op->has_b2, p.bias_steps = op->bias_steps;
+      p.blk_chunks = op->blk_chunks, p.k_tail_pad = op->k_tail_pad, p.smem_aconst_off = op->smem_aconst_off;
       p.b_resident = op->b_resident, p.num_stages = op->num_stages, p.stage_bytes = op->stage_bytes;
       p.bias_count = (int) op->bias_count;
       p.smem_b_off = op->smem_b_off, p.smem_bias_off = op->smem_bias_off, p.smem_a_off = op->smem_a_off;
@@ -727,16 +817,19 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_bias(qnnp_operator_t op, 
   return qnnp_status_success;
 }
 QNNP_EXPORT unsigned long long qnnp_cuda_launch_count(void) { return g_lib.launches.load(); }
-QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int out[20]) {
+QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int folded, int bias_steps, int out[24]) {
   IgemmPlan pl;
   const int optin = g_lib.initialized ? g_lib.max_smem_optin : 232448;  // B200: 227 KB opt-in
-  if (!plan_igemm(k, n, groups, optin, &pl)) return 0;
-  const int v[20] = {pl.K, pl.nkc, pl.skc, pl.k_stages, pl.mt, pl.n_tiles, pl.n_tile, pl.n_mma, pl.has_corr, pl.b_resident,
+  if (!plan_igemm(k, n, groups, optin, folded, bias_steps, &pl)) return 0;
+  const int v[24] = {pl.K, pl.nkc, pl.skc, pl.k_stages, pl.mt, pl.n_tiles, pl.n_tile, pl.n_mma, pl.has_corr, pl.b_resident,
                      pl.num_stages, pl.stage_bytes, pl.staging_bytes, pl.bias_bytes, pl.smem_b_off, pl.smem_bias_off,
-                     pl.smem_a_off, pl.smem_stage_off, pl.smem_total, pl.bulk_capable};
-  for (int i = 0; i < 20; i++) out[i] = v[i];
+                     pl.smem_a_off, pl.smem_stage_off, pl.smem_total, pl.bulk_capable, pl.folded, pl.bias_steps,
+                     pl.blk_chunks, pl.good};
+  for (int i = 0; i < 24; i++) out[i] = v[i];
   return 1;
 }
+/* 1 if the operator runs in folded mode (bias + zero-point correction on the tensor core), 0 otherwise. */
+QNNP_EXPORT int qnnp_cuda_debug_operator_is_folded(qnnp_operator_t op) { return op != nullptr && op->folded ? 1 : 0; }
 QNNP_EXPORT void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer) { g_lib.dbg_acc = device_buffer; }
 QNNP_EXPORT const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op) {
   if (op == nullptr) return "null";
