@@ -1,0 +1,269 @@
+// q8dwconv 3x3, streaming dp4a kernel for sm_100a (stride 1 or 2, dilation 1, channels % 4 == 0).
+//
+// Replaces q8dwconv_ukernel_up8x9__sse2 (reference src/q8dwconv/up8x9-sse2.c:14-372) driven by
+// src/operator-run.c:659-681; the indirection buffer (src/indirection.c:81-132) is never built.
+//
+// Same integers as the reference:  acc[c] = bias'[c] + sum_taps a_tap[c] * (w_tap[c] - kzp), padded taps read izp.
+//
+// Why this shape.  Depthwise layers move 2 bytes per output (stride 1) with 9 MACs each: at HBM speed an SM must
+// retire ~11 outputs per clock, i.e. it has ~11 issue slots per output.  One IMAD per tap (9) plus byte
+// extraction does not fit.  Here a thread owns 4 channels x 4 output columns and streams down the input rows:
+//   * the 4 channel bytes of up to 9 neighbouring pixels are transposed (PRMT) into "3 taps of one channel"
+//     words, so that ONE dp4a does the three horizontal taps of a kernel row;  (w - kzp) is 9-bit, so the
+//     weights are split once at create time into two s8 halves (w-kzp = A + B) — or one operand when it fits;
+//   * each input row is loaded once per thread and feeds the (up to) three output rows it belongs to, whose
+//     partial sums rotate through registers; a finished row is requantised (fused Q31) and stored.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "q8_dwconv_sm100.cuh"
+#include "sm100_ptx.cuh"
+
+namespace q8 {
+
+namespace {
+
+constexpr int TX = 4;  // output columns per thread
+
+template <int RQ>
+__device__ __forceinline__ int32_t dws_requant(int32_t n, const Q8Requant& rq) {
+  if constexpr (RQ == 0) {
+    return q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
+  } else if constexpr (RQ == 1) {
+    int32_t t = q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
+    t = max(t, rq.qmin);
+    return min(t, rq.qmax);
+  } else if constexpr (RQ == 2) {
+    return q8_requant_shift0(n, rq.multiplier, rq.zero_point, rq.qmin, rq.qmax);
+  } else if constexpr (RQ == 4) {
+    int32_t t = q8_requant_fused_shift1_unclamped(n, rq.multiplier, rq.c_neg);
+    t = max(t, rq.qmin);
+    return min(t, rq.qmax);
+  } else {
+    return q8_requant_exact_slow(n, rq);
+  }
+}
+
+// u8 activations x (s8 | u8) weights, 4-way dot product accumulate
+template <bool W_UNSIGNED>
+__device__ __forceinline__ int32_t dot4(uint32_t a, uint32_t w, int32_t acc) {
+  int32_t r;
+  if constexpr (W_UNSIGNED) {
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(w), "r"(acc));
+  } else {
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(w), "r"(acc));
+  }
+  return r;
+}
+
+// 4x4 byte transpose: in: a,b,c,d = 4 pixels x 4 channels; out: t[ch] = (a[ch], b[ch], c[ch], d[ch])
+__device__ __forceinline__ void transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&t)[4]) {
+  const uint32_t ab_lo = __byte_perm(a, b, 0x5140);  // a0 b0 a1 b1
+  const uint32_t ab_hi = __byte_perm(a, b, 0x7362);  // a2 b2 a3 b3
+  const uint32_t cd_lo = __byte_perm(c, d, 0x5140);
+  const uint32_t cd_hi = __byte_perm(c, d, 0x7362);
+  t[0] = __byte_perm(ab_lo, cd_lo, 0x5410);  // a0 b0 c0 d0
+  t[1] = __byte_perm(ab_lo, cd_lo, 0x7632);  // a1 b1 c1 d1
+  t[2] = __byte_perm(ab_hi, cd_hi, 0x5410);
+  t[3] = __byte_perm(ab_hi, cd_hi, 0x7632);
+}
+
+// Windows of one input row: win[x][c] = bytes (pixel x*S + 0, +1, +2, <don't care>) of channel c.
+template <int S>
+__device__ __forceinline__ void row_windows(const DwStreamParams& p, const uint8_t* img, int iy, int ix0, uint32_t fill,
+                                            uint32_t (&win)[TX][4]) {
+  constexpr int NC = (TX - 1) * S + 3;
+  uint32_t col[NC];
+  const bool rowok = (unsigned) iy < (unsigned) p.in_h;
+  const uint8_t* rowp = img + (size_t) (rowok ? iy : 0) * p.in_w * p.in_stride;
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    const int ix = ix0 + j;
+    const bool ok = rowok && (unsigned) ix < (unsigned) p.in_w;
+    col[j] = ok ? __ldg(reinterpret_cast<const uint32_t*>(rowp + (size_t) ix * p.in_stride)) : fill;
+  }
+  uint32_t t0[4];
+  transpose4(col[0], col[1], col[2], col[3], t0);
+  if constexpr (S == 1) {
+    // pixels 4,5 only as a pair per channel: u01 = (p4c0, p5c0, p4c1, p5c1), u23 = (p4c2, p5c2, p4c3, p5c3)
+    const uint32_t u01 = __byte_perm(col[4], col[5], 0x5140);
+    const uint32_t u23 = __byte_perm(col[4], col[5], 0x7362);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint32_t u = (c < 2) ? u01 : u23;
+      win[0][c] = t0[c];                                                       // p0 p1 p2 (p3)
+      win[1][c] = __byte_perm(t0[c], u, (c & 1) ? 0x6321 : 0x4321);            // p1 p2 p3 (p4)
+      win[2][c] = __byte_perm(t0[c], u, (c & 1) ? 0x7632 : 0x5432);            // p2 p3 p4 p5
+      win[3][c] = __byte_perm(t0[c], u, (c & 1) ? 0x0763 : 0x0543);            // p3 p4 p5 (x)
+    }
+  } else {
+    uint32_t t1[4];
+    transpose4(col[4], col[5], col[6], col[7], t1);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      win[0][c] = t0[c];                                                       // p0 p1 p2 (p3)
+      win[1][c] = __byte_perm(t0[c], t1[c], 0x0432);                           // p2 p3 p4 (x)
+      win[2][c] = t1[c];                                                       // p4 p5 p6 (p7)
+      win[3][c] = __byte_perm(t1[c], col[8], 0x0032 | ((4 + c) << 8));         // p6 p7 p8 (x)
+    }
+  }
+}
+
+// WMODE 0: one s8 operand; 1: one u8 operand (kzp == 0); 2: two s8 operands (w - kzp = A + B)
+template <int WMODE>
+__device__ __forceinline__ void accumulate_row(const uint32_t (&win)[TX][4], const uint32_t (&wa)[4], const uint32_t (&wb)[4],
+                                               int32_t (&acc)[TX][4]) {
+#pragma unroll
+  for (int x = 0; x < TX; x++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      acc[x][c] = dot4<WMODE == 1>(win[x][c], wa[c], acc[x][c]);
+      if constexpr (WMODE == 2) acc[x][c] = dot4<false>(win[x][c], wb[c], acc[x][c]);
+    }
+  }
+}
+
+template <int RQ>
+__device__ __forceinline__ void finish_row(const DwStreamParams& p, uint8_t* obase, int oy, int oy_end, int ox0,
+                                           int32_t (&acc)[TX][4], const int4 bias) {
+  if (oy >= 0 && oy < oy_end) {
+    uint8_t* orow = obase + (size_t) oy * p.out_w * p.out_stride;
+#pragma unroll
+    for (int x = 0; x < TX; x++) {
+      if (ox0 + x < p.out_w) {
+        const uint32_t packed = pack_sat_u8x4(dws_requant<RQ>(acc[x][0], p.rq), dws_requant<RQ>(acc[x][1], p.rq),
+                                              dws_requant<RQ>(acc[x][2], p.rq), dws_requant<RQ>(acc[x][3], p.rq));
+        *reinterpret_cast<uint32_t*>(orow + (size_t) (ox0 + x) * p.out_stride) = packed;
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < TX; x++) acc[x][0] = bias.x, acc[x][1] = bias.y, acc[x][2] = bias.z, acc[x][3] = bias.w;
+}
+
+template <int S, int WMODE, int RQ>
+__global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __grid_constant__ DwStreamParams p) {
+  const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.total_threads) return;
+  const int cg = (int) (idx % p.cgroups);
+  long long r = idx / p.cgroups;
+  const int xs = (int) (r % p.xstrips);
+  r /= p.xstrips;
+  const int yc = (int) (r % p.ychunks);
+  const long long n = r / p.ychunks;
+  const int c0 = cg * 4;
+  const int ox0 = xs * TX;
+  const int oy0 = yc * p.tyc;
+  const int rows = min(p.tyc, p.out_h - oy0);
+
+  // per-channel packed taps: word = (w[ky][0], w[ky][1], w[ky][2], 0) for channel c, operand A (and B)
+  uint32_t wa[3][4], wb[3][4];
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.wa + (size_t) ky * p.c_pad + c0));
+    wa[ky][0] = a.x, wa[ky][1] = a.y, wa[ky][2] = a.z, wa[ky][3] = a.w;
+    if constexpr (WMODE == 2) {
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.wb + (size_t) ky * p.c_pad + c0));
+      wb[ky][0] = b.x, wb[ky][1] = b.y, wb[ky][2] = b.z, wb[ky][3] = b.w;
+    } else {
+      wb[ky][0] = wb[ky][1] = wb[ky][2] = wb[ky][3] = 0;
+    }
+  }
+  const int4 bias = __ldg(reinterpret_cast<const int4*>(p.bias + c0));
+
+  const uint8_t* img = p.in + (size_t) n * p.in_h * p.in_w * p.in_stride + c0;
+  uint8_t* obase = p.out + (size_t) n * p.out_h * p.out_w * p.out_stride + c0;
+  const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
+  const int ix0 = ox0 * S - p.pad_left;
+  const int iy0 = oy0 * S - p.pad_top;
+  const int oy_end = oy0 + rows;
+  const int T = (rows - 1) * S + 3;  // input rows touched by this thread
+
+  if constexpr (S == 1) {
+    // input row t feeds output rows o = t - ky; o lives in slot o % 3; o completes at t = o + 2.
+    int32_t acc[3][TX][4];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+      for (int x = 0; x < TX; x++) acc[s][x][0] = bias.x, acc[s][x][1] = bias.y, acc[s][x][2] = bias.z, acc[s][x][3] = bias.w;
+    for (int t3 = 0; t3 < T; t3 += 3) {
+#pragma unroll
+      for (int v = 0; v < 3; v++) {
+        const int t = t3 + v;
+        if (t < T) {
+          uint32_t win[TX][4];
+          row_windows<1>(p, img, iy0 + t, ix0, fill, win);
+#pragma unroll
+          for (int ky = 0; ky < 3; ky++) accumulate_row<WMODE>(win, wa[ky], wb[ky], acc[(v - ky + 3) % 3]);
+          // (contributions to rows o < 0 land in slots that are reset below before their first real use)
+          finish_row<RQ>(p, obase, oy0 + t - 2 < oy0 ? -1 : oy0 + t - 2, oy_end, ox0, acc[(v + 1) % 3], bias);
+        }
+      }
+    }
+  } else {
+    // stride 2: even input row t = 2u feeds ky=0 of o=u and ky=2 of o=u-1 (which completes); odd t = 2u+1 feeds ky=1 of o=u.
+    int32_t acc[2][TX][4];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+      for (int x = 0; x < TX; x++) acc[s][x][0] = bias.x, acc[s][x][1] = bias.y, acc[s][x][2] = bias.z, acc[s][x][3] = bias.w;
+    for (int t4 = 0; t4 < T; t4 += 4) {
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const int t = t4 + v;
+        if (t < T) {
+          uint32_t win[TX][4];
+          row_windows<2>(p, img, iy0 + t, ix0, fill, win);
+          if ((v & 1) == 0) {
+            accumulate_row<WMODE>(win, wa[0], wb[0], acc[v >> 1]);
+            accumulate_row<WMODE>(win, wa[2], wb[2], acc[1 - (v >> 1)]);
+            const int o = (t >> 1) - 1;
+            finish_row<RQ>(p, obase, o < 0 ? -1 : oy0 + o, oy_end, ox0, acc[1 - (v >> 1)], bias);
+          } else {
+            accumulate_row<WMODE>(win, wa[1], wb[1], acc[v >> 1]);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int S, int WMODE>
+cudaError_t launch_rq(const DwStreamParams& p, cudaStream_t stream) {
+  const int threads = 128;
+  const unsigned blocks = (unsigned) ((p.total_threads + threads - 1) / threads);
+  switch (p.rq_mode) {
+    case 0: q8_dwconv3x3_stream_kernel<S, WMODE, 0><<<blocks, threads, 0, stream>>>(p); break;
+    case 1: q8_dwconv3x3_stream_kernel<S, WMODE, 1><<<blocks, threads, 0, stream>>>(p); break;
+    case 2: q8_dwconv3x3_stream_kernel<S, WMODE, 2><<<blocks, threads, 0, stream>>>(p); break;
+    case 4: q8_dwconv3x3_stream_kernel<S, WMODE, 4><<<blocks, threads, 0, stream>>>(p); break;
+    default: q8_dwconv3x3_stream_kernel<S, WMODE, 3><<<blocks, threads, 0, stream>>>(p); break;
+  }
+  return cudaGetLastError();
+}
+
+template <int S>
+cudaError_t launch_wmode(const DwStreamParams& p, cudaStream_t stream) {
+  switch (p.wmode) {
+    case 0: return launch_rq<S, 0>(p, stream);
+    case 1: return launch_rq<S, 1>(p, stream);
+    default: return launch_rq<S, 2>(p, stream);
+  }
+}
+
+}  // namespace
+
+// Requirements (checked by the caller): 3x3, dilation 1, stride_h == stride_w in {1, 2}, channels % 4 == 0,
+// input/output base and pixel strides multiples of 4.
+cudaError_t launch_q8_dwconv3x3_stream(DwStreamParams p, cudaStream_t stream) {
+  p.cgroups = p.channels / 4;
+  p.xstrips = (p.out_w + TX - 1) / TX;
+  // rows per thread: enough to amortise the 2-row halo, small enough to keep every SM busy on small images
+  p.tyc = p.out_h >= 56 ? 16 : (p.out_h >= 14 ? 14 : p.out_h);
+  p.ychunks = (p.out_h + p.tyc - 1) / p.tyc;
+  p.total_threads = (long long) p.batch * p.ychunks * p.xstrips * p.cgroups;
+  if (p.total_threads == 0) return cudaSuccess;
+  return p.stride == 1 ? launch_wmode<1>(p, stream) : launch_wmode<2>(p, stream);
+}
+
+}  // namespace q8

@@ -159,6 +159,9 @@ struct qnnp_operator {
   int smem_b_off = 0, smem_bias_off = 0, smem_a_off = 0, smem_stage_off = 0, staging_bytes = 0, smem_total = 0;
   bool bulk_capable = false;
   int c_pad = 0;  // dw
+  uint32_t* d_dw_wa = nullptr;  // dw streaming kernel: packed taps, operands A and B
+  uint32_t* d_dw_wb = nullptr;
+  int dw_wmode = 0;
 
   // setup-time
   size_t batch = 0, in_h = 0, in_w = 0, out_h = 0, out_w = 0;
@@ -178,6 +181,8 @@ void free_operator(qnnp_operator* op) {
   if (op == nullptr) return;
   cudaFree(op->d_weights);
   cudaFree(op->d_bias);
+  cudaFree(op->d_dw_wa);
+  cudaFree(op->d_dw_wb);
   cudaFree(op->d_in);
   cudaFree(op->d_out);
   delete op;
@@ -255,11 +260,17 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
     const int v = atoi(e);
     if (v >= 1 && v < mt_max) mt_max = v;
   }
-  struct Cand { int mt, skc, resident, stages, stage_bytes, staging; long long inflight; bool ok; };
-  Cand best{0, 0, 0, 0, 0, 0, -1, false};
-  for (int mt = mt_max; mt >= 1 && !best.ok; mt--) {
+  // Candidates: every (mt, skc).  Feasible = >= 3 ring stages and >= 64 KB of loads in flight (or 3 whole items).
+  // Among feasible plans minimise the synchronisation cost per 128-row tile, (1 + k_stages) / mt  — one item-level
+  // hand-over plus one ring hand-over per K stage, amortised over mt sub-tiles — with >= 64 contiguous bytes per row
+  // and stage (skc >= 4) so that global reads stay sector-efficient; ties go to the larger stage.
+  struct Cand { int mt, skc, resident, stages, stage_bytes, staging; long long inflight; bool ok; double cost; };
+  Cand best{0, 0, 0, 0, 0, 0, -1, false, 1e30};
+  const int skc_min = pl->nkc < 4 ? pl->nkc : 4;
+  for (int mt = mt_max; mt >= 1; mt--) {
     const int staging = pl->bulk_capable ? mt * q8::kTileM * (int) goc : 0;  // per epilogue pair
-    for (int skc = pl->nkc < 8 ? pl->nkc : 8; skc >= 2; skc = (skc > 4 ? 4 : skc - 2)) {
+    for (int skc = pl->nkc; skc >= 2; skc -= 2) {
+      if (skc > 16 && skc != pl->nkc && (skc % 8) != 0) continue;  // prune the search
       const int a_stage = mt * skc * q8::kChunkBytes;
       const long long fixed = pl->bias_bytes + aconst_bytes + 2LL * staging;
       const int resident = ((long long) pl->w_total + fixed + 3LL * a_stage <= smem_max) ? 1 : 0;
@@ -270,9 +281,11 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
       if (stages > q8::kMaxStages) stages = q8::kMaxStages;
       if (stages < 2) continue;
       const long long inflight = (long long) stages * a_stage;
-      const bool ok = stages >= 3 && (inflight >= 64 * 1024 || (long long) stages * skc >= pl->nkc * 3LL);
-      if (ok || inflight > best.inflight) best = Cand{mt, skc, resident, stages, stage_bytes, staging, inflight, ok};
-      if (ok) break;
+      const int k_stages = (int) ceil_div(pl->nkc, skc);
+      const bool ok = stages >= 3 && skc >= skc_min && (inflight >= 64 * 1024 || stages >= 3 * k_stages);
+      const double cost = (1.0 + k_stages) / mt - 1e-9 * stage_bytes;
+      const bool better = (ok && !best.ok) || (ok == best.ok && (ok ? cost < best.cost : inflight > best.inflight));
+      if (better) best = Cand{mt, skc, resident, stages, stage_bytes, staging, inflight, ok, cost};
     }
   }
   if (best.mt == 0) return false;
@@ -415,16 +428,47 @@ enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int3
   const size_t C = op->groups;
   op->c_pad = (int) round_up(C, 4);
   std::vector<int32_t> w32((size_t) 9 * op->c_pad, 0), fbias(op->c_pad, 0);
+  bool fits_s8 = true;
   for (size_t c = 0; c < C; c++) {
-    for (int t = 0; t < 9; t++) w32[(size_t) t * op->c_pad + c] = (int32_t) kernel[c * 9 + t] - (int32_t) op->kzp;
+    for (int t = 0; t < 9; t++) {
+      const int32_t d = (int32_t) kernel[c * 9 + t] - (int32_t) op->kzp;
+      w32[(size_t) t * op->c_pad + c] = d;
+      if (d < -128 || d > 127) fits_s8 = false;
+    }
     fbias[c] = fold_bias(bias[c], 9, op->izp, op->kzp, kernel + c * 9);
   }
+  // streaming dp4a kernel: per channel and kernel row one word (tap kx=0, kx=1, kx=2, 0).
+  //   kzp == 0            -> u8 weights as they are                      (wmode 1)
+  //   every w-kzp in s8   -> one s8 operand                               (wmode 0)
+  //   otherwise           -> w - kzp = A + B, A = floor(d/2), B = d - A   (wmode 2; both in [-128, 127] since kzp >= 1)
+  op->dw_wmode = op->kzp == 0 ? 1 : (fits_s8 ? 0 : 2);
+  std::vector<uint32_t> wa((size_t) 3 * op->c_pad, 0), wb((size_t) 3 * op->c_pad, 0);
+  for (size_t c = 0; c < C; c++)
+    for (int ky = 0; ky < 3; ky++) {
+      uint32_t a = 0, b = 0;
+      for (int kx = 0; kx < 3; kx++) {
+        const int32_t d = w32[(size_t) (ky * 3 + kx) * op->c_pad + c];
+        int32_t da = d, db = 0;
+        if (op->dw_wmode == 2) {
+          da = d >> 1;  // floor
+          db = d - da;
+        }
+        a |= (uint32_t) (uint8_t) da << (8 * kx);
+        b |= (uint32_t) (uint8_t) db << (8 * kx);
+      }
+      wa[(size_t) ky * op->c_pad + c] = a;
+      wb[(size_t) ky * op->c_pad + c] = b;
+    }
   op->weights_bytes = w32.size() * sizeof(int32_t);
   op->bias_count = fbias.size();
   cudaError_t e = cudaMalloc(&op->d_weights, op->weights_bytes);
   if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, fbias.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_dw_wa, wa.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_dw_wb, wb.size() * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, w32.data(), op->weights_bytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), fbias.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_dw_wa, wa.data(), wa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_dw_wb, wb.data(), wb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   return map_cuda(e, "uploading depthwise weights");
 }
 
@@ -513,7 +557,22 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       cv = pow2_align((uintptr_t) op->in_stride, cv);
       cv = pow2_align((uintptr_t) op->out_stride, cv);
       cv = pow2_align((uintptr_t) op->groups, cv);
-      e = q8::launch_q8_dwconv3x3(p, cv == 4 ? 4 : 1, stream);
+      const bool stream_ok = cv == 4 && op->dil_h == 1 && op->dil_w == 1 && op->stride_h == op->stride_w &&
+          (op->stride_h == 1 || op->stride_h == 2) && getenv("QNNP_CUDA_DW_GENERIC") == nullptr;
+      if (stream_ok) {
+        q8::DwStreamParams sp{};
+        sp.in = in, sp.out = out;
+        sp.wa = op->d_dw_wa, sp.wb = op->d_dw_wb, sp.bias = op->d_bias;
+        sp.in_stride = (long long) op->in_stride, sp.out_stride = (long long) op->out_stride;
+        sp.batch = (int) op->batch, sp.channels = (int) op->groups, sp.c_pad = op->c_pad;
+        sp.in_h = (int) op->in_h, sp.in_w = (int) op->in_w, sp.out_h = (int) op->out_h, sp.out_w = (int) op->out_w;
+        sp.stride = (int) op->stride_h, sp.pad_top = (int) op->pad_top, sp.pad_left = (int) op->pad_left;
+        sp.wmode = op->dw_wmode, sp.izp = op->izp;
+        sp.rq = op->rq, sp.rq_mode = op->rq_mode;
+        e = q8::launch_q8_dwconv3x3_stream(sp, stream);
+      } else {
+        e = q8::launch_q8_dwconv3x3(p, cv == 4 ? 4 : 1, stream);
+      }
       break;
     }
     case kKindDirect: {
