@@ -14,8 +14,8 @@
 // extra B row of ones (accumulator column n_tile).
 //
 // Structure (one CTA per SM, 672 threads):
-//   warps 0-7   epilogue pair 0 (TMEM stage 0, even work items)   TMEM -> regs -> Q31 requant -> uint8 -> global
-//   warps 8-15  epilogue pair 1 (TMEM stage 1, odd work items)
+//   warps 0-15  epilogue: TMEM -> regs -> Q31 requant -> uint8 -> 32-byte global stores; every warp works on every
+//               work item (lane quarter = warp % 4; the 4 warps of a quarter interleave column blocks)
 //   warp  16    TMEM allocation + UMMA issue (one lane)
 //   warps 17-20 loaders: cp.async global -> smem, canonical K-major no-swizzle layout [sub-tile][k-chunk][row][16 B]
 // A work item is `mt` (<= 8) consecutive 128-row sub-tiles x one n-tile: the sub-tiles' accumulators sit side
@@ -32,7 +32,7 @@
 namespace q8 {
 
 constexpr int kEpiWarps = 16;
-constexpr int kEpiPairThreads = 256;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;
 constexpr int kLoadWarp0 = kMmaWarp + 1;
 constexpr int kLoadWarps = 4;
@@ -165,6 +165,107 @@ __device__ __forceinline__ void load_a_conv(const IgemmParams& p, const Item& it
   }
 }
 
+// Small-channel 3x3 convolution (the MobileNetV2 stem: 3 input channels, K = 27): with dense pixels and
+// dilation_w == 1 the three taps of a kernel row are ONE contiguous run of kw*gic = 9 bytes, at an arbitrary byte
+// alignment.  A thread gathers its pixel's three runs with 3 aligned 32-bit loads each (funnel-shifted into
+// place), packs the 27 bytes of the K row in registers and writes them with two 16-byte shared stores.  Up to
+// four pixels (sub-tiles) are in flight per thread so that the loads overlap.  Taps outside the image read izp.
+constexpr int kRun = 9;
+
+__device__ __forceinline__ void run9_load(const uint8_t* src, uint32_t (&w)[3]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src) & 3;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(src - a);
+  w[0] = __ldg(base);
+  w[1] = __ldg(base + 1);
+  w[2] = __ldg(base + 2);
+}
+
+__device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid) {
+  constexpr int NB = 2;  // pixels (sub-tiles) in flight per thread
+  const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
+  for (int j0 = 0; j0 < it.mt_eff; j0 += NB) {
+    uint32_t w[NB][3][3];
+    // per run: bits 0-1 = byte alignment of the source, bits 2-3 = state (0: in bounds, 1: all padding, 2: edge)
+    uint32_t info[NB] = {0, 0};
+#pragma unroll
+    for (int jj = 0; jj < NB; jj++) {
+      const long long m = it.m0 + (long long) (j0 + jj) * kTileM + ltid;
+      const bool live = (j0 + jj) < it.mt_eff && m < p.M;
+      const long long mm = live ? m : 0;
+      const int ox = (int) (mm % p.out_w);
+      const long long t = mm / p.out_w;
+      const int oy = (int) (t % p.out_h);
+      const long long n = t / p.out_h;
+      const int iy0 = oy * p.stride_h - p.pad_top, ix0 = ox * p.stride_w - p.pad_left;
+      const bool full = ix0 >= 0 && ix0 + p.kw <= p.in_w;
+      const uint8_t* img = p.in + ((size_t) n * p.in_h * p.in_w + (full ? ix0 : 0)) * 3;
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+        const int iy = iy0 + ky * p.dil_h;
+        const bool rowok = (unsigned) iy < (unsigned) p.in_h;
+        const uint32_t st = (!live || !rowok) ? 1u : (full ? 0u : 2u);
+        const uint8_t* src = img + (size_t) (rowok ? iy : 0) * p.in_w * 3;
+        info[jj] |= (((uint32_t) reinterpret_cast<uintptr_t>(src) & 3u) | (st << 2)) << (4 * ky);
+        if (st == 0) {
+          run9_load(src, w[jj][ky]);
+        } else {
+          w[jj][ky][0] = w[jj][ky][1] = w[jj][ky][2] = fill;
+        }
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < NB; jj++) {
+      if (j0 + jj < it.mt_eff) {
+        uint32_t r[3][3];
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+          const uint32_t inf = info[jj] >> (4 * ky);
+          const uint32_t st = (inf >> 2) & 3u;
+          if (st == 0) {
+            const uint32_t sh = (inf & 3u) * 8;
+            r[ky][0] = __funnelshift_r(w[jj][ky][0], w[jj][ky][1], sh);
+            r[ky][1] = __funnelshift_r(w[jj][ky][1], w[jj][ky][2], sh);
+            r[ky][2] = (w[jj][ky][2] >> sh) & 0xFFu;
+          } else if (st == 1) {
+            r[ky][0] = fill, r[ky][1] = fill, r[ky][2] = fill & 0xFFu;
+          } else {
+            // left/right edge: assemble the run byte by byte (rare: one pixel per image row)
+            const long long m = it.m0 + (long long) (j0 + jj) * kTileM + ltid;
+            const int ox = (int) (m % p.out_w);
+            const long long t = m / p.out_w;
+            const int oy = (int) (t % p.out_h);
+            const long long n = t / p.out_h;
+            const int ix0 = ox * p.stride_w - p.pad_left;
+            const int iy = oy * p.stride_h - p.pad_top + ky * p.dil_h;
+            const uint8_t* rowp = p.in + ((size_t) n * p.in_h + iy) * p.in_w * 3;
+            uint32_t b0 = 0, b1 = 0, b2 = 0;
+            for (int i = 0; i < kRun; i++) {
+              const int ix = ix0 + i / 3;
+              const uint32_t v = ((unsigned) ix < (unsigned) p.in_w) ? (uint32_t) __ldg(rowp + (size_t) ix * 3 + i % 3)
+                                                                      : (uint32_t) p.izp;
+              if (i < 4) b0 |= v << (8 * i);
+              else if (i < 8) b1 |= v << (8 * (i - 4));
+              else b2 |= v;
+            }
+            r[ky][0] = b0, r[ky][1] = b1, r[ky][2] = b2;
+          }
+        }
+        // K row: bytes [0,9) = ky 0, [9,18) = ky 1, [18,27) = ky 2, [27,32) = padding (zero weights)
+        const uint32_t k0 = r[0][0], k1 = r[0][1];
+        const uint32_t k2 = r[0][2] | (r[1][0] << 8);
+        const uint32_t k3 = __funnelshift_r(r[1][0], r[1][1], 24);
+        const uint32_t k4 = (r[1][1] >> 24) | (r[1][2] << 8) | (r[2][0] << 16);
+        const uint32_t k5 = __funnelshift_r(r[2][0], r[2][1], 16);
+        const uint32_t k6 = (r[2][1] >> 16) | (r[2][2] << 16);
+        const uint32_t d = a_stage + (uint32_t) ((j0 + jj) * p.skc) * kChunkBytes + (uint32_t) ltid * 16;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + kChunkBytes), "r"(k4), "r"(k5), "r"(k6), "r"(0u)
+                     : "memory");
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void copy_bytes16(uint32_t dst, const uint8_t* src, int bytes, int ltid) {
   for (int o = ltid * 16; o < bytes; o += kLoadThreads * 16) cp_async<16>(dst + o, src + o);
 }
@@ -181,7 +282,9 @@ __device__ __forceinline__ int32_t requant_dev(int32_t n, const IgemmParams& p) 
     const uint32_t lo = (uint32_t) p.rq.c_pos | ((uint32_t) n & 0x80000000u);
     const int64_t addend = (int64_t) (((uint64_t) (uint32_t) (p.rq.c_pos >> 32) << 32) | lo);
     const int32_t hi = (int32_t) (((int64_t) n * (int64_t) p.rq.multiplier + addend) >> 32);
-    int32_t y = (hi + (n >> 31)) >> (p.rq.shift - 1);
+    // final arithmetic shift by (shift-1): as a multiply-high by 2^(33-shift) it runs on the FMA pipe and
+    // leaves the (busier) ALU pipe to LOP3 / LEA / I2IP
+    int32_t y = p.shift_mul != 0 ? __mulhi(hi + (n >> 31), p.shift_mul) : ((hi + (n >> 31)) >> (p.rq.shift - 1));
     if constexpr (RQ == 1) {
       y = max(y, p.rq.qmin);
       y = min(y, p.rq.qmax);
@@ -203,6 +306,9 @@ __device__ __noinline__ void store_row_partial(uint8_t* dst, uint32_t w0, uint32
                                                int vec) {
   const uint32_t w[4] = {w0, w1, w2, w3};
   int i = 0;
+  if (vec >= 8) {
+    for (; i + 8 <= valid; i += 8) *reinterpret_cast<uint2*>(dst + i) = make_uint2(w[i >> 2], w[(i >> 2) + 1]);
+  }
   if (vec >= 4) {
     for (; i + 4 <= valid; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = w[i >> 2];
   }
@@ -212,39 +318,36 @@ __device__ __noinline__ void store_row_partial(uint8_t* dst, uint32_t w0, uint32
 struct EpiCtx {
   uint32_t tlane;      // TMEM address of this warp's lane quarter, column 0 of the accumulator stage
   uint32_t bias_base;  // smem address of this (group, n_tile)'s folded biases ("ones" mode)
-  uint32_t staging;    // smem staging buffer of the epilogue pair (bulk mode)
   uint8_t* obase;      // out + g*goc + nt*n_tile
   long long item;
   int row;             // row inside a sub-tile == TMEM lane
   int n_valid;         // valid output channels of this n-tile
-  bool bulk;
 };
 
-// 16 output bytes (4 packed words) of row `m`, columns [c0, c0+16) of the n-tile
-__device__ __forceinline__ void emit16(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, uint32_t w0,
-                                       uint32_t w1, uint32_t w2, uint32_t w3) {
+// NB output bytes (NB/4 packed words, NB = 16 or 32) of row m, columns [c0, c0+NB) of the n-tile, straight from
+// registers: a thread owns NB contiguous bytes of its pixel, i.e. whole 32-byte sectors when NB == 32.
+template <int NB>
+__device__ __forceinline__ void emit(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, const uint32_t* w) {
   const int valid = e.n_valid - c0;
-  if (valid <= 0) return;
-  if (e.bulk) {
-    // staging = dense image of the item's output rows (pitch goc; goc % 4 == 0 guaranteed by the host)
-    const uint32_t s = e.staging + (uint32_t) (j * kTileM + e.row) * p.goc + c0;
-    if (valid >= 16 && (p.goc & 15) == 0) {
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-    } else {
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(s), "r"(w0) : "memory");
-      if (valid > 4) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 4), "r"(w1) : "memory");
-      if (valid > 8) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 8), "r"(w2) : "memory");
-      if (valid > 12) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 12), "r"(w3) : "memory");
+  const long long m = it.m0 + (long long) j * kTileM + e.row;
+  if (valid <= 0 || m >= p.M) return;
+  uint8_t* dst = e.obase + (size_t) m * p.out_stride + c0;
+  if constexpr (NB == 32) {
+    if (valid >= 32 && p.out_vec >= 32) {
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                   "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                   : "memory");
+      return;
     }
-  } else {
-    const long long m = it.m0 + (long long) j * kTileM + e.row;
-    if (m < p.M) {
-      uint8_t* dst = e.obase + (size_t) m * p.out_stride + c0;
-      if (valid >= 16 && p.out_vec == 16) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w0, w1, w2, w3);
-      } else {
-        store_row_partial(dst, w0, w1, w2, w3, valid < 16 ? valid : 16, p.out_vec);
-      }
+  }
+#pragma unroll
+  for (int h = 0; h < NB / 16; h++) {
+    const int v = valid - 16 * h;
+    if (v <= 0) break;
+    if (v >= 16 && p.out_vec >= 16) {
+      *reinterpret_cast<uint4*>(dst + 16 * h) = make_uint4(w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]);
+    } else {
+      store_row_partial(dst + 16 * h, w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3], v < 16 ? v : 16, p.out_vec);
     }
   }
 }
@@ -291,25 +394,25 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
   for (int t = 0; t < W / 4; t++)
     w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p), requant_dev<RQ>(v[4 * t + 1], p), requant_dev<RQ>(v[4 * t + 2], p),
                          requant_dev<RQ>(v[4 * t + 3], p));  // saturation to [0,255] is the clamp when qmin=0,qmax=255
-#pragma unroll
-  for (int t = 0; t < W / 16; t++) emit16(p, it, e, j, c0 + 16 * t, w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
+  emit<W>(p, it, e, j, c0, w);
 }
 
-// One epilogue warp: lane quarter q of the accumulator, every second (sub-tile, column-block) unit of the item.
+// One epilogue warp = lane quarter q (warp % 4) of the accumulator; the four warps that share a quarter take
+// every fourth (sub-tile, column-block) unit of the item.
 template <int RQ, bool FOLDED>
-__device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
+__device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& it, const EpiCtx& e, int rank) {
   constexpr int W = FOLDED ? 32 : 16;
   const int full = p.n_tile / W;            // full-width units per sub-tile
   const int per_sub = full + ((p.n_tile % W) ? 1 : 0);
   const int units = it.mt_eff * per_sub;
-  int j = half / per_sub, c = half - j * per_sub;
-  for (int u = half; u < units; u += 2) {
+  int j = rank / per_sub, c = rank - j * per_sub;
+  for (int u = rank; u < units; u += 4) {
     if (c < full) {
       epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W);
     } else {
       epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
     }
-    c += 2;
+    c += 4;
     while (c >= per_sub) {
       c -= per_sub;
       ++j;
@@ -318,11 +421,11 @@ __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& 
 }
 
 template <int RQ>
-__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
+__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Item& it, const EpiCtx& e, int rank) {
   if (p.folded) {
-    epilogue_item<RQ, true>(p, it, e, half);
+    epilogue_item<RQ, true>(p, it, e, rank);
   } else {
-    epilogue_item<RQ, false>(p, it, e, half);
+    epilogue_item<RQ, false>(p, it, e, rank);
   }
 }
 
@@ -348,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
-      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiPairThreads);
+      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiThreads);
     }
     mbar_init(smem_u32(&ctl.b_full), kLoadThreads);
     fence_mbar_init();
@@ -387,6 +490,8 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
         const uint32_t a_stage = a_smem + stage * p.stage_bytes;
         if constexpr (MODE == kModeGemm) {
           load_a_gemm<VEC>(p, it, ks, a_stage, ltid);
+        } else if constexpr (VEC == 0) {
+          load_a_conv_run9(p, it, a_stage, ltid);  // K = 27 fits one stage
         } else {
           load_a_conv<VEC>(p, it, ks, a_stage, ltid);
         }
@@ -471,55 +576,35 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     }
   } else {
     // ===================================== epilogue =====================================
-    const int pair = warp >> 3;          // 0 or 1 == TMEM stage
-    const int pw = warp & 7;
-    const int q = pw & 3, half = pw >> 2;
+    // All 16 warps work on every item (TMEM stage = item parity); nothing but the two TMEM barriers
+    // synchronises them, so a warp that finishes its units moves straight on to the next item.
+    const int q = warp & 3, rank = warp >> 2;
     const int lane = tid & 31;
-    const int pair_tid = tid & (kEpiPairThreads - 1);
-    const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
-    mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem
-    long long li = pair;
-    bool bulk_pending = false;
-    for (long long item = first + pair * step; item < p.total_items; item += 2 * step, li += 2) {
+    mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem ("ones" mode reads them)
+    long long li = 0;
+    for (long long item = first; item < p.total_items; item += step, li++) {
       const Item it = decode_item(p, item);
-      const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
-      if (p.out_mode == 1) {
-        // the previous bulk store of this pair must have finished reading the staging buffer
-        if (pair_tid == 0 && bulk_pending) bulk_wait_read<0>();
-        named_bar_sync(1 + pair, kEpiPairThreads);
-      }
-      mbar_wait(smem_u32(&ctl.tmem_full[pair]), (uint32_t) ((li >> 1) & 1));
+      const int as = (int) (li & 1);
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), (uint32_t) ((li >> 1) & 1));
       tc_fence_after_sync();
       EpiCtx e;
-      e.tlane = tmem_base + pair * kMaxNMma + ((uint32_t) (q * 32) << 16);
+      e.tlane = tmem_base + as * kMaxNMma + ((uint32_t) (q * 32) << 16);
       e.bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
-      e.staging = staging;
       e.obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
       e.item = item;
       e.row = q * 32 + lane;
       e.n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
-      e.bulk = bulk;
       switch (p.rq_mode) {
-        case 0: epilogue_dispatch<0>(p, it, e, half); break;
-        case 1: epilogue_dispatch<1>(p, it, e, half); break;
-        case 2: epilogue_dispatch<2>(p, it, e, half); break;
-        case 4: epilogue_dispatch<4>(p, it, e, half); break;
-        default: epilogue_dispatch<3>(p, it, e, half); break;
+        case 0: epilogue_dispatch<0>(p, it, e, rank); break;
+        case 1: epilogue_dispatch<1>(p, it, e, rank); break;
+        case 2: epilogue_dispatch<2>(p, it, e, rank); break;
+        case 4: epilogue_dispatch<4>(p, it, e, rank); break;
+        default: epilogue_dispatch<3>(p, it, e, rank); break;
       }
-      // the accumulator stage may be overwritten by the next-but-one work item
+      // this warp is done reading the accumulator stage; the UMMA warp may reuse it once all 16 have arrived
       tc_fence_before_sync();
-      mbar_arrive(smem_u32(&ctl.tmem_empty[pair]));
-      if (p.out_mode == 1) {
-        fence_proxy_async_smem();
-        named_bar_sync(1 + pair, kEpiPairThreads);
-        if (bulk && pair_tid == 0) {
-          bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, (uint32_t) (it.mt_eff * kTileM * p.goc));
-          bulk_commit();
-          bulk_pending = true;
-        }
-      }
+      mbar_arrive(smem_u32(&ctl.tmem_empty[as]));
     }
-    if (pair_tid == 0 && bulk_pending) bulk_wait<0>();
   }
 
   tc_fence_before_sync();
@@ -556,6 +641,7 @@ cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, int grid, c
       case 16: return launch_one<kModeConv, 16>(p, grid, stream);
       case 8: return launch_one<kModeConv, 8>(p, grid, stream);
       case 4: return launch_one<kModeConv, 4>(p, grid, stream);
+      case 0: return launch_one<kModeConv, 0>(p, grid, stream);  // 9-byte row runs (3x3, 3 channels)
       default: return launch_one<kModeConv, 1>(p, grid, stream);
     }
   }

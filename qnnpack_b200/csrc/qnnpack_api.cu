@@ -268,7 +268,7 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
   Cand best{0, 0, 0, 0, 0, 0, -1, false, 1e30};
   const int skc_min = pl->nkc < 4 ? pl->nkc : 4;
   for (int mt = mt_max; mt >= 1; mt--) {
-    const int staging = pl->bulk_capable ? mt * q8::kTileM * (int) goc : 0;  // per epilogue pair
+    const int staging = 0;  // (outputs go straight from registers to global memory)
     for (int skc = pl->nkc; skc >= 2; skc -= 2) {
       if (skc > 16 && skc != pl->nkc && (skc % 8) != 0) continue;  // prune the search
       const int a_stage = mt * skc * q8::kChunkBytes;
@@ -518,24 +518,27 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.b_resident = op->b_resident, p.num_stages = op->num_stages, p.stage_bytes = op->stage_bytes;
       p.bias_count = (int) op->bias_count;
       p.smem_b_off = op->smem_b_off, p.smem_bias_off = op->smem_bias_off, p.smem_a_off = op->smem_a_off;
-      p.smem_stage_off = op->smem_stage_off, p.staging_bytes = op->staging_bytes, p.smem_total = op->smem_total;
+      p.smem_total = op->smem_total;
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
       p.rq_mode = op->rq_mode;
       // output path
-      const bool bulk = op->bulk_capable && op->out_stride == op->goc && ((uintptr_t) out % 16) == 0 &&
-          getenv("QNNP_CUDA_NO_BULK_STORE") == nullptr;
-      p.out_mode = bulk ? 1 : 0;
-      int ov = pow2_align((uintptr_t) out, 16);
+      int ov = pow2_align((uintptr_t) out, 32);
       ov = pow2_align((uintptr_t) op->out_stride, ov);
       if (op->groups > 1) ov = pow2_align((uintptr_t) op->goc, ov);  // group offset g*goc (tile offsets are multiples of 16)
       p.out_vec = ov;
+      p.shift_mul = (op->rq.fused && op->rq.shift >= 3) ? (int) (1u << (33 - op->rq.shift)) : 0;
       // loader vector width
       int vec = pow2_align((uintptr_t) in, 16);
       vec = pow2_align((uintptr_t) op->in_stride, vec);
       vec = pow2_align((uintptr_t) op->gic, vec);
       if (vec < 4) vec = 1;
       const int mode = op->kind == kKindIgemmGemm ? q8::kModeGemm : q8::kModeConv;
+      // 3x3 over 3 dense channels (MobileNetV2 stem): the taps of a kernel row are one 9-byte run
+      if (mode == q8::kModeConv && vec == 1 && op->kh == 3 && op->kw == 3 && op->gic == 3 && op->dil_w == 1 &&
+          op->in_stride == 3 && op->k_stages == 1 && op->in_w >= 3 && ((uintptr_t) in % 4) == 0 &&
+          (M * 0 + op->batch * op->in_h * op->in_w * 3) % 4 == 0 && getenv("QNNP_CUDA_NO_RUN9") == nullptr)
+        vec = 0;
       long long grid = p.total_items < g_lib.num_sms ? p.total_items : g_lib.num_sms;
       e = q8::launch_q8_igemm(p, mode, vec, (int) grid, stream);
       break;
