@@ -69,18 +69,21 @@ __device__ __forceinline__ void transpose4(uint32_t a, uint32_t b, uint32_t c, u
 }
 
 // Windows of one input row: win[x][c] = bytes (pixel x*S + 0, +1, +2, <don't care>) of channel c.
+// rp = address of (row iy, column ix0) — may lie outside the image for padded rows/columns, in which case it is
+// never dereferenced; colmask bit j = column ix0 + j is inside the image.
 template <int S>
-__device__ __forceinline__ void row_windows(const DwStreamParams& p, const uint8_t* img, int iy, int ix0, uint32_t fill,
-                                            uint32_t (&win)[TX][4]) {
+__device__ __forceinline__ void row_windows(const uint8_t* rp, const int (&coff)[(TX - 1) * S + 3], bool rowok, uint32_t colmask,
+                                            uint32_t fill, uint32_t (&win)[TX][4]) {
   constexpr int NC = (TX - 1) * S + 3;
+  constexpr uint32_t kAll = (1u << NC) - 1;
   uint32_t col[NC];
-  const bool rowok = (unsigned) iy < (unsigned) p.in_h;
-  const uint8_t* rowp = img + (size_t) (rowok ? iy : 0) * p.in_w * p.in_stride;
+  if (rowok && colmask == kAll) {
 #pragma unroll
-  for (int j = 0; j < NC; j++) {
-    const int ix = ix0 + j;
-    const bool ok = rowok && (unsigned) ix < (unsigned) p.in_w;
-    col[j] = ok ? __ldg(reinterpret_cast<const uint32_t*>(rowp + (size_t) ix * p.in_stride)) : fill;
+    for (int j = 0; j < NC; j++) col[j] = __ldg(reinterpret_cast<const uint32_t*>(rp + coff[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+      col[j] = (rowok && ((colmask >> j) & 1u)) ? __ldg(reinterpret_cast<const uint32_t*>(rp + coff[j])) : fill;
   }
   uint32_t t0[4];
   transpose4(col[0], col[1], col[2], col[3], t0);
@@ -171,11 +174,21 @@ __global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __gri
   }
   const int4 bias = __ldg(reinterpret_cast<const int4*>(p.bias + c0));
 
-  const uint8_t* img = p.in + (size_t) n * p.in_h * p.in_w * p.in_stride + c0;
   uint8_t* obase = p.out + (size_t) n * p.out_h * p.out_w * p.out_stride + c0;
   const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
   const int ix0 = ox0 * S - p.pad_left;
   const int iy0 = oy0 * S - p.pad_top;
+  constexpr int NC = (TX - 1) * S + 3;
+  int coff[NC];
+  uint32_t colmask = 0;
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    coff[j] = j * (int) p.in_stride;
+    colmask |= ((unsigned) (ix0 + j) < (unsigned) p.in_w ? 1u : 0u) << j;
+  }
+  const long long row_pitch = (long long) p.in_w * p.in_stride;
+  // address of (row iy0, column ix0); advanced by one row pitch per input row
+  const uint8_t* rp = p.in + ((long long) n * p.in_h + iy0) * row_pitch + (long long) ix0 * p.in_stride + c0;
   const int oy_end = oy0 + rows;
   const int T = (rows - 1) * S + 3;  // input rows touched by this thread
 
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __gri
         const int t = t3 + v;
         if (t < T) {
           uint32_t win[TX][4];
-          row_windows<1>(p, img, iy0 + t, ix0, fill, win);
+          row_windows<1>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, win);
 #pragma unroll
           for (int ky = 0; ky < 3; ky++) accumulate_row<WMODE>(win, wa[ky], wb[ky], acc[(v - ky + 3) % 3]);
           // (contributions to rows o < 0 land in slots that are reset below before their first real use)
@@ -213,7 +226,7 @@ __global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __gri
         const int t = t4 + v;
         if (t < T) {
           uint32_t win[TX][4];
-          row_windows<2>(p, img, iy0 + t, ix0, fill, win);
+          row_windows<2>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, win);
           if ((v & 1) == 0) {
             accumulate_row<WMODE>(win, wa[0], wb[0], acc[v >> 1]);
             accumulate_row<WMODE>(win, wa[2], wb[2], acc[1 - (v >> 1)]);

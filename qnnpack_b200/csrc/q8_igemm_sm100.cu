@@ -23,8 +23,10 @@
 // over up to 1024 rows — essential for the narrow (N = 16..96) projection layers.
 // Pipelines: smem ring full/empty mbarriers (loaders <-> UMMA), two TMEM accumulator stages
 // full/empty (UMMA <-> epilogue pairs).  int32 accumulators never leave TMEM/registers.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "q8_igemm_sm100.cuh"
 #include "sm100_ptx.cuh"
@@ -37,7 +39,9 @@ constexpr int kMmaWarp = kEpiWarps;
 constexpr int kLoadWarp0 = kMmaWarp + 1;
 constexpr int kLoadWarps = 4;
 constexpr int kLoadThreads = kLoadWarps * 32;
-constexpr int kThreads = (kLoadWarp0 + kLoadWarps) * 32;  // 672
+constexpr int kStoreWarp = kLoadWarp0 + kLoadWarps;       // lanes 0/1: bulk-store issue for epilogue pair 0/1
+constexpr int kThreads = (kStoreWarp + 1) * 32;           // 704
+constexpr int kEpiPairThreads = 256;
 constexpr int kTmemCols = 512;
 
 struct __align__(8) SmemCtl {
@@ -46,6 +50,8 @@ struct __align__(8) SmemCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t b_full;
+  uint64_t out_full[2];  // epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
+  uint64_t out_free[2];  // store thread -> epilogue pair: the staging buffer may be overwritten
   uint32_t tmem_base;
 };
 
@@ -266,6 +272,20 @@ __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Ite
   }
 }
 
+// 1x1 / fully-connected through the TMA: the activation matrix is described once (host side) as a 3-D tensor
+// {16 bytes of K, M rows, K/16 chunks}; ONE instruction then lands a [chunks][128 rows][16 B] box — exactly the
+// no-swizzle UMMA operand image of a sub-tile — and signals the stage barrier with its byte count.  No per-lane
+// address arithmetic, rows beyond M and chunks beyond K are zero-filled by the hardware.
+constexpr int kVecTma = 32;  // value of the VEC template parameter that selects this loader
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
 __device__ __forceinline__ void copy_bytes16(uint32_t dst, const uint8_t* src, int bytes, int ltid) {
   for (int o = ltid * 16; o < bytes; o += kLoadThreads * 16) cp_async<16>(dst + o, src + o);
 }
@@ -318,19 +338,40 @@ __device__ __noinline__ void store_row_partial(uint8_t* dst, uint32_t w0, uint32
 struct EpiCtx {
   uint32_t tlane;      // TMEM address of this warp's lane quarter, column 0 of the accumulator stage
   uint32_t bias_base;  // smem address of this (group, n_tile)'s folded biases ("ones" mode)
+  uint32_t staging;    // smem staging buffer of the epilogue pair (bulk mode)
   uint8_t* obase;      // out + g*goc + nt*n_tile
   long long item;
   int row;             // row inside a sub-tile == TMEM lane
   int n_valid;         // valid output channels of this n-tile
+  bool bulk;           // this item's output goes through the staging buffer and one bulk (1-D TMA) store
 };
 
-// NB output bytes (NB/4 packed words, NB = 16 or 32) of row m, columns [c0, c0+NB) of the n-tile, straight from
-// registers: a thread owns NB contiguous bytes of its pixel, i.e. whole 32-byte sectors when NB == 32.
+// NB output bytes (NB/4 packed words, NB = 16 or 32) of row m, columns [c0, c0+NB) of the n-tile.
+// bulk: into the dense smem image of the item's output rows (pitch goc, goc % 4 == 0), later written by ONE
+// cp.async.bulk per item — the TMA engine produces full-width global writes, which strided per-thread stores do not.
 template <int NB>
 __device__ __forceinline__ void emit(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, const uint32_t* w) {
   const int valid = e.n_valid - c0;
+  if (valid <= 0) return;
+  if (e.bulk) {
+    const uint32_t s = e.staging + (uint32_t) (j * kTileM + e.row) * p.goc + c0;
+#pragma unroll
+    for (int h = 0; h < NB / 16; h++) {
+      const int v = valid - 16 * h;
+      if (v >= 16 && (p.goc & 15) == 0) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s + 16 * h), "r"(w[4 * h]), "r"(w[4 * h + 1]),
+                     "r"(w[4 * h + 2]), "r"(w[4 * h + 3])
+                     : "memory");
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (4 * k < v) asm volatile("st.shared.b32 [%0], %1;" ::"r"(s + 16 * h + 4 * k), "r"(w[4 * h + k]) : "memory");
+      }
+    }
+    return;
+  }
   const long long m = it.m0 + (long long) j * kTileM + e.row;
-  if (valid <= 0 || m >= p.M) return;
+  if (m >= p.M) return;
   uint8_t* dst = e.obase + (size_t) m * p.out_stride + c0;
   if constexpr (NB == 32) {
     if (valid >= 32 && p.out_vec >= 32) {
@@ -397,22 +438,22 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
   emit<W>(p, it, e, j, c0, w);
 }
 
-// One epilogue warp = lane quarter q (warp % 4) of the accumulator; the four warps that share a quarter take
-// every fourth (sub-tile, column-block) unit of the item.
+// One epilogue warp = lane quarter q (warp % 4) of its pair's accumulator stage; the two warps of a pair that share
+// a quarter take alternate (sub-tile, column-block) units of the item.
 template <int RQ, bool FOLDED>
-__device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& it, const EpiCtx& e, int rank) {
+__device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
   constexpr int W = FOLDED ? 32 : 16;
   const int full = p.n_tile / W;            // full-width units per sub-tile
   const int per_sub = full + ((p.n_tile % W) ? 1 : 0);
   const int units = it.mt_eff * per_sub;
-  int j = rank / per_sub, c = rank - j * per_sub;
-  for (int u = rank; u < units; u += 4) {
+  int j = half / per_sub, c = half - j * per_sub;
+  for (int u = half; u < units; u += 2) {
     if (c < full) {
       epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W);
     } else {
       epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
     }
-    c += 4;
+    c += 2;
     while (c >= per_sub) {
       c -= per_sub;
       ++j;
@@ -421,11 +462,11 @@ __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& 
 }
 
 template <int RQ>
-__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Item& it, const EpiCtx& e, int rank) {
+__device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
   if (p.folded) {
-    epilogue_item<RQ, true>(p, it, e, rank);
+    epilogue_item<RQ, true>(p, it, e, half);
   } else {
-    epilogue_item<RQ, false>(p, it, e, rank);
+    epilogue_item<RQ, false>(p, it, e, half);
   }
 }
 
@@ -433,7 +474,8 @@ __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const It
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int VEC>
-__global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+    q8_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ SmemCtl ctl;
 
@@ -446,14 +488,19 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < p.num_stages; s++) {
-      mbar_init(smem_u32(&ctl.full[s]), kLoadThreads);
+      // arrivals per stage: the 128 cp.async loaders, or one expect_tx arrival (TMA) plus the loaders when they stream B
+      mbar_init(smem_u32(&ctl.full[s]), VEC == kVecTma ? (p.b_resident ? 1 : 1 + kLoadThreads) : kLoadThreads);
       mbar_init(smem_u32(&ctl.empty[s]), 1);
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
-      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiThreads);
+      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiPairThreads);
     }
     mbar_init(smem_u32(&ctl.b_full), kLoadThreads);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&ctl.out_full[s]), kEpiPairThreads);
+      mbar_init(smem_u32(&ctl.out_free[s]), 1);
+    }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<kTmemCols>(smem_u32(&ctl.tmem_base));
@@ -486,9 +533,20 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
     for (long long item = first; item < p.total_items; item += step) {
       const Item it = decode_item(p, item);
       for (int ks = 0; ks < p.k_stages; ks++) {
+        if constexpr (VEC == kVecTma) {
+          if (p.b_resident && ltid != 0) continue;  // one thread drives the TMA; the others only matter when B streams
+        }
         mbar_wait(smem_u32(&ctl.empty[stage]), phase ^ 1);
         const uint32_t a_stage = a_smem + stage * p.stage_bytes;
-        if constexpr (MODE == kModeGemm) {
+        if constexpr (VEC == kVecTma) {
+          if (ltid == 0) {
+            const uint32_t bar = smem_u32(&ctl.full[stage]);
+            mbar_arrive_expect_tx(bar, (uint32_t) (it.mt_eff * p.skc) * kChunkBytes);
+            for (int j = 0; j < it.mt_eff; j++)
+              tma_load_3d(a_stage + (uint32_t) (j * p.skc) * kChunkBytes, &tmap_a, 0, (int) (it.m0 + (long long) j * kTileM),
+                          ks * p.skc, bar);
+          }
+        } else if constexpr (MODE == kModeGemm) {
           load_a_gemm<VEC>(p, it, ks, a_stage, ltid);
         } else if constexpr (VEC == 0) {
           load_a_conv_run9(p, it, a_stage, ltid);  // K = 27 fits one stage
@@ -502,8 +560,12 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
               p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.blk_chunks + (size_t) ks * p.skc) * p.n_mma * 16;
           copy_bytes16(a_stage + p.mt * p.skc * kChunkBytes, wsrc, cs * p.n_mma * 16, ltid);
         }
-        fence_proxy_async_smem();  // st.shared fills (padding taps / byte path) -> UMMA reads
-        cp_async_mbar_arrive_noinc(smem_u32(&ctl.full[stage]));
+        if constexpr (VEC == kVecTma) {
+          if (!p.b_resident) cp_async_mbar_arrive_noinc(smem_u32(&ctl.full[stage]));
+        } else {
+          fence_proxy_async_smem();  // st.shared fills (padding taps / byte path) -> UMMA reads
+          cp_async_mbar_arrive_noinc(smem_u32(&ctl.full[stage]));
+        }
         if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1;
@@ -574,36 +636,65 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
         umma_commit(smem_u32(&ctl.tmem_full[as]));
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // ===================================== epilogue =====================================
-    // All 16 warps work on every item (TMEM stage = item parity); nothing but the two TMEM barriers
-    // synchronises them, so a warp that finishes its units moves straight on to the next item.
-    const int q = warp & 3, rank = warp >> 2;
+    // Pair 0 (warps 0-7) handles even work items in TMEM stage 0, pair 1 (warps 8-15) odd items in stage 1.
+    // A pair's eight warps never synchronise with each other: they hand finished output tiles to the store
+    // thread through two mbarriers.
+    const int pair = warp >> 3;
+    const int q = warp & 3, half = (warp >> 2) & 1;
     const int lane = tid & 31;
+    const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
     mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem ("ones" mode reads them)
-    long long li = 0;
-    for (long long item = first; item < p.total_items; item += step, li++) {
+    long long li = pair;
+    for (long long item = first + pair * step; item < p.total_items; item += 2 * step, li += 2) {
       const Item it = decode_item(p, item);
-      const int as = (int) (li & 1);
-      mbar_wait(smem_u32(&ctl.tmem_full[as]), (uint32_t) ((li >> 1) & 1));
+      const uint32_t k = (uint32_t) (li >> 1);  // this pair's item counter
+      const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
+      if (p.out_mode == 1) mbar_wait(smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1);  // staging buffer is free again
+      mbar_wait(smem_u32(&ctl.tmem_full[pair]), k & 1);
       tc_fence_after_sync();
       EpiCtx e;
-      e.tlane = tmem_base + as * kMaxNMma + ((uint32_t) (q * 32) << 16);
+      e.tlane = tmem_base + pair * kMaxNMma + ((uint32_t) (q * 32) << 16);
       e.bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
+      e.staging = staging;
       e.obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
       e.item = item;
       e.row = q * 32 + lane;
       e.n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
+      e.bulk = bulk;
       switch (p.rq_mode) {
-        case 0: epilogue_dispatch<0>(p, it, e, rank); break;
-        case 1: epilogue_dispatch<1>(p, it, e, rank); break;
-        case 2: epilogue_dispatch<2>(p, it, e, rank); break;
-        case 4: epilogue_dispatch<4>(p, it, e, rank); break;
-        default: epilogue_dispatch<3>(p, it, e, rank); break;
+        case 0: epilogue_dispatch<0>(p, it, e, half); break;
+        case 1: epilogue_dispatch<1>(p, it, e, half); break;
+        case 2: epilogue_dispatch<2>(p, it, e, half); break;
+        case 4: epilogue_dispatch<4>(p, it, e, half); break;
+        default: epilogue_dispatch<3>(p, it, e, half); break;
       }
-      // this warp is done reading the accumulator stage; the UMMA warp may reuse it once all 16 have arrived
+      // done reading the accumulator stage: the UMMA warp may reuse it once the pair's 8 warps have arrived
       tc_fence_before_sync();
-      mbar_arrive(smem_u32(&ctl.tmem_empty[as]));
+      mbar_arrive(smem_u32(&ctl.tmem_empty[pair]));
+      if (p.out_mode == 1) {
+        fence_proxy_async_smem();  // staging writes (generic proxy) -> bulk copy (async proxy)
+        mbar_arrive(smem_u32(&ctl.out_full[pair]));
+      }
+    }
+  } else if (warp == kStoreWarp) {
+    // ===================================== output stores =====================================
+    const int pair = tid & 31;
+    if (pair < 2 && p.out_mode == 1) {
+      const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
+      uint32_t k = 0;
+      for (long long item = first + pair * step; item < p.total_items; item += 2 * step, k++) {
+        const Item it = decode_item(p, item);
+        mbar_wait(smem_u32(&ctl.out_full[pair]), k & 1);
+        if (it.m0 + (long long) it.mt_eff * kTileM <= p.M) {
+          bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, (uint32_t) (it.mt_eff * kTileM * p.goc));
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+        mbar_arrive(smem_u32(&ctl.out_free[pair]));
+      }
+      bulk_wait<0>();
     }
   }
 
@@ -620,29 +711,37 @@ __global__ void __launch_bounds__(kThreads, 1) q8_igemm_kernel(const __grid_cons
 // host launcher
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int VEC>
-static cudaError_t launch_one(const IgemmParams& p, int grid, cudaStream_t stream) {
+static cudaError_t launch_one(const IgemmParams& p, const CUtensorMap& tmap, int grid, cudaStream_t stream) {
   auto kern = q8_igemm_kernel<MODE, VEC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, p.smem_total, stream>>>(p);
+  kern<<<grid, kThreads, p.smem_total, stream>>>(p, tmap);
   return cudaGetLastError();
 }
 
-cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, int grid, cudaStream_t stream) {
+// vec: 16/8/4/1 = cp.async piece size, 0 = 9-byte row runs (3x3 over 3 channels), 32 = TMA (gemm mode; `tmap` valid)
+cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, int grid, cudaStream_t stream) {
+  alignas(64) CUtensorMap tmap;
+  if (tmap_a != nullptr) {
+    memcpy(&tmap, tmap_a, sizeof(tmap));
+  } else {
+    memset(&tmap, 0, sizeof(tmap));
+  }
   if (mode == kModeGemm) {
     switch (vec) {
-      case 16: return launch_one<kModeGemm, 16>(p, grid, stream);
-      case 8: return launch_one<kModeGemm, 8>(p, grid, stream);
-      case 4: return launch_one<kModeGemm, 4>(p, grid, stream);
-      default: return launch_one<kModeGemm, 1>(p, grid, stream);
+      case 32: return launch_one<kModeGemm, 32>(p, tmap, grid, stream);
+      case 16: return launch_one<kModeGemm, 16>(p, tmap, grid, stream);
+      case 8: return launch_one<kModeGemm, 8>(p, tmap, grid, stream);
+      case 4: return launch_one<kModeGemm, 4>(p, tmap, grid, stream);
+      default: return launch_one<kModeGemm, 1>(p, tmap, grid, stream);
     }
   } else {
     switch (vec) {
-      case 16: return launch_one<kModeConv, 16>(p, grid, stream);
-      case 8: return launch_one<kModeConv, 8>(p, grid, stream);
-      case 4: return launch_one<kModeConv, 4>(p, grid, stream);
-      case 0: return launch_one<kModeConv, 0>(p, grid, stream);  // 9-byte row runs (3x3, 3 channels)
-      default: return launch_one<kModeConv, 1>(p, grid, stream);
+      case 16: return launch_one<kModeConv, 16>(p, tmap, grid, stream);
+      case 8: return launch_one<kModeConv, 8>(p, tmap, grid, stream);
+      case 4: return launch_one<kModeConv, 4>(p, tmap, grid, stream);
+      case 0: return launch_one<kModeConv, 0>(p, tmap, grid, stream);  // 9-byte row runs (3x3, 3 channels)
+      default: return launch_one<kModeConv, 1>(p, tmap, grid, stream);
     }
   }
 }

@@ -53,12 +53,13 @@ struct IgemmParams {
   int num_stages; // A(+B) ring depth
   int stage_bytes;
   int bias_count; // ints in `bias`
+  int out_mode;   // 1: full items leave through the smem staging buffer + one bulk store; 0: per-thread global stores
   int out_vec;    // widest power-of-two (<= 32) dividing output base address, pixel stride and channel offsets
   int shift_mul;  // 2^(33 - shift) when the final shift can be done as a multiply-high (shift >= 3), else 0
   int rq_mode;    // 0: fused shift>=2, no clamp; 1: fused shift>=2 + clamp; 2: shift==0; 3: exact slow; 4: fused shift==1
 
   // smem carve-up (byte offsets into dynamic smem, 1024-aligned base)
-  int smem_b_off, smem_bias_off, smem_a_off, smem_total;
+  int smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, staging_bytes, smem_total;
 
   int izp, kzp;
   Q8Requant rq;

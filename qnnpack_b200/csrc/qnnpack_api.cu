@@ -10,6 +10,7 @@
 // What changes: weights are packed for UMMA instead of for 4x4c2 SSE2 tiles (src/qnnpack/pack.h), no
 // indirection buffer is ever built (src/indirection.c), run = one kernel launch on a CUDA stream.
 // There is no CPU fallback: without a compute-capability-10.x device initialisation fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <pthread.h>
@@ -29,7 +30,7 @@
 #include "q8_igemm_sm100.cuh"
 
 namespace q8 {
-cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, int grid, cudaStream_t stream);
+cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, int grid, cudaStream_t stream);
 }
 
 #define QNNP_EXPORT extern "C" __attribute__((visibility("default")))
@@ -106,6 +107,35 @@ void init_once() {
 void bind_device() {
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess || cur != g_lib.device) cudaSetDevice(g_lib.device);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn) p;
+  }();
+  return fn;
+}
+
+// Activation matrix [M][in_stride] (first K bytes of a row used) as {16 B of K, M rows, K/16 chunks}; box = {16, 128, skc}.
+bool make_tmap_a(CUtensorMap* tm, const uint8_t* in, size_t M, size_t in_stride, int K, int skc) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t gdim[3] = {16, (cuuint64_t) M, (cuuint64_t) (K / 16)};
+  const cuuint64_t gstride[2] = {(cuuint64_t) in_stride, 16};
+  const cuuint32_t box[3] = {16, (cuuint32_t) q8::kTileM, (cuuint32_t) skc};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool is_device_pointer(const void* ptr) {
@@ -268,7 +298,7 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
   Cand best{0, 0, 0, 0, 0, 0, -1, false, 1e30};
   const int skc_min = pl->nkc < 4 ? pl->nkc : 4;
   for (int mt = mt_max; mt >= 1; mt--) {
-    const int staging = 0;  // (outputs go straight from registers to global memory)
+    const int staging = pl->bulk_capable ? mt * q8::kTileM * (int) goc : 0;  // per epilogue pair
     for (int skc = pl->nkc; skc >= 2; skc -= 2) {
       if (skc > 16 && skc != pl->nkc && (skc % 8) != 0) continue;  // prune the search
       const int a_stage = mt * skc * q8::kChunkBytes;
@@ -518,11 +548,14 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.b_resident = op->b_resident, p.num_stages = op->num_stages, p.stage_bytes = op->stage_bytes;
       p.bias_count = (int) op->bias_count;
       p.smem_b_off = op->smem_b_off, p.smem_bias_off = op->smem_bias_off, p.smem_a_off = op->smem_a_off;
-      p.smem_total = op->smem_total;
+      p.smem_stage_off = op->smem_stage_off, p.staging_bytes = op->staging_bytes, p.smem_total = op->smem_total;
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
       p.rq_mode = op->rq_mode;
       // output path
+      const bool bulk = op->bulk_capable && op->out_stride == op->goc && ((uintptr_t) out % 16) == 0 &&
+          getenv("QNNP_CUDA_NO_BULK_STORE") == nullptr;
+      p.out_mode = bulk ? 1 : 0;
       int ov = pow2_align((uintptr_t) out, 32);
       ov = pow2_align((uintptr_t) op->out_stride, ov);
       if (op->groups > 1) ov = pow2_align((uintptr_t) op->goc, ov);  // group offset g*goc (tile offsets are multiples of 16)
@@ -539,8 +572,16 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
           op->in_stride == 3 && op->k_stages == 1 && op->in_w >= 3 && ((uintptr_t) in % 4) == 0 &&
           (M * 0 + op->batch * op->in_h * op->in_w * 3) % 4 == 0 && getenv("QNNP_CUDA_NO_RUN9") == nullptr)
         vec = 0;
+      // 1x1 / FC with 16-byte aligned rows: the TMA loads the activation tiles
+      alignas(64) CUtensorMap tmap;
+      const void* tmap_ptr = nullptr;
+      if (mode == q8::kModeGemm && vec == 16 && op->groups == 1 && (op->K % 16) == 0 && op->skc <= 256 && M < (1ull << 31) &&
+          getenv("QNNP_CUDA_NO_TMA") == nullptr && make_tmap_a(&tmap, in, M, op->in_stride, op->K, op->skc)) {
+        vec = 32;
+        tmap_ptr = &tmap;
+      }
       long long grid = p.total_items < g_lib.num_sms ? p.total_items : g_lib.num_sms;
-      e = q8::launch_q8_igemm(p, mode, vec, (int) grid, stream);
+      e = q8::launch_q8_igemm(p, mode, vec, tmap_ptr, (int) grid, stream);
       break;
     }
     case kKindDw3x3: {
