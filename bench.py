@@ -227,30 +227,50 @@ def b200_main(args, rank, local_rank, world):
     layer_ms = [statistics.fmean(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)) for i in range(nl)]
 
     # ---- e2e: batch from pinned host memory, logits back to the host, inside the timed region ---------
+    # The public API is driven the way a serving loop would drive it: step i+1's images are copied host->device
+    # on a copy stream (into the other of two device input buffers) while step i computes; the first layer is
+    # re-setup each step with the buffer that holds its images (setup only records pointers); logits return
+    # over the compute stream.  Every step's H2D, 53 C-ABI runs and D2H are inside the timed region.
     e2e = None
     if not args.no_e2e:
         x_host = torch.randint(0, 256, (B * 224 * 224 * 3,), dtype=torch.uint8).pin_memory()
         y_host = torch.empty(B * 1000, dtype=torch.uint8).pin_memory()
+        x_dev = [x_in, torch.empty_like(x_in)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        free_ev = [torch.cuda.Event() for _ in range(2)]
+        stem, stem_op = stack.layers[0], stack.ops[0]
 
-        def e2e_step():
-            x_in.copy_(x_host, non_blocking=True)
-            stack.run(asynchronous=True)
-            y_host.copy_(logits_dev, non_blocking=True)
-            stream.synchronize()  # the caller owns the result when the call returns
+        def e2e_steps(n):
+            for s in range(n):
+                b = s % 2
+                with torch.cuda.stream(copy_stream):
+                    if s >= 2:
+                        copy_stream.wait_event(free_ev[b])      # the stem of step s-2 has consumed this buffer
+                    x_dev[b].copy_(x_host, non_blocking=True)
+                    h2d_done[b].record(copy_stream)
+                stream.wait_event(h2d_done[b])
+                st = lib.setup_convolution(stem_op, B, stem.h, stem.h, x_dev[b].data_ptr(), stem.cin, buf_a.data_ptr(), stem.cout)
+                assert st == 0
+                stack.run(asynchronous=True, hook=lambda i, after, b=b: free_ev[b].record(stream) if (after and i == 0) else None)
+                y_host.copy_(logits_dev, non_blocking=True)
+            stream.synchronize()  # the caller owns every result when the loop returns
 
-        e2e_step()
+        e2e_steps(2)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_steps(args.steps)
         e1.record(stream)
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * args.steps / (float(t.item()) * 1e-3), "unit": "images/s",
-               "h2d_bytes_per_step": int(x_host.numel()), "d2h_bytes_per_step": int(y_host.numel())}
+               "h2d_bytes_per_step": int(x_host.numel()), "d2h_bytes_per_step": int(y_host.numel()),
+               "note": "H2D of step i+1 overlaps the compute of step i (two device input buffers, copy stream)"}
+        # restore the stem's input for anything that runs afterwards
+        lib.setup_convolution(stem_op, B, stem.h, stem.h, x_in.data_ptr(), stem.cin, buf_a.data_ptr(), stem.cout)
 
     if rank != 0:
         if world > 1:

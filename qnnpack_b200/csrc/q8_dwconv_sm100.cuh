@@ -39,6 +39,7 @@ struct DwStreamParams {
   int wmode;            // 0: one s8 operand, 1: one u8 operand (kzp == 0), 2: two s8 operands (w - kzp = A + B)
   int izp;
   int rq_mode;
+  int shift_mul;        // see requant_dev.cuh
   Q8Requant rq;
 };
 

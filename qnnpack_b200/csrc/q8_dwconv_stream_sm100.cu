@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "q8_dwconv_sm100.cuh"
+#include "requant_dev.cuh"
 #include "sm100_ptx.cuh"
 
 namespace q8 {
@@ -24,25 +25,6 @@ namespace q8 {
 namespace {
 
 constexpr int TX = 4;  // output columns per thread
-
-template <int RQ>
-__device__ __forceinline__ int32_t dws_requant(int32_t n, const Q8Requant& rq) {
-  if constexpr (RQ == 0) {
-    return q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
-  } else if constexpr (RQ == 1) {
-    int32_t t = q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
-    t = max(t, rq.qmin);
-    return min(t, rq.qmax);
-  } else if constexpr (RQ == 2) {
-    return q8_requant_shift0(n, rq.multiplier, rq.zero_point, rq.qmin, rq.qmax);
-  } else if constexpr (RQ == 4) {
-    int32_t t = q8_requant_fused_shift1_unclamped(n, rq.multiplier, rq.c_neg);
-    t = max(t, rq.qmin);
-    return min(t, rq.qmax);
-  } else {
-    return q8_requant_exact_slow(n, rq);
-  }
-}
 
 // u8 activations x (s8 | u8) weights, 4-way dot product accumulate
 template <bool W_UNSIGNED>
@@ -113,14 +95,16 @@ __device__ __forceinline__ void row_windows(const uint8_t* rp, const int (&coff)
 }
 
 // WMODE 0: one s8 operand; 1: one u8 operand (kzp == 0); 2: two s8 operands (w - kzp = A + B)
-template <int WMODE>
+// INIT: this is the first kernel row of a new output row -> start from the folded bias instead of accumulating
+template <int WMODE, bool INIT>
 __device__ __forceinline__ void accumulate_row(const uint32_t (&win)[TX][4], const uint32_t (&wa)[4], const uint32_t (&wb)[4],
-                                               int32_t (&acc)[TX][4]) {
+                                               int32_t (&acc)[TX][4], const int4 bias) {
+  const int32_t b[4] = {bias.x, bias.y, bias.z, bias.w};
 #pragma unroll
   for (int x = 0; x < TX; x++) {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      acc[x][c] = dot4<WMODE == 1>(win[x][c], wa[c], acc[x][c]);
+      acc[x][c] = dot4<WMODE == 1>(win[x][c], wa[c], INIT ? b[c] : acc[x][c]);
       if constexpr (WMODE == 2) acc[x][c] = dot4<false>(win[x][c], wb[c], acc[x][c]);
     }
   }
@@ -128,24 +112,23 @@ __device__ __forceinline__ void accumulate_row(const uint32_t (&win)[TX][4], con
 
 template <int RQ>
 __device__ __forceinline__ void finish_row(const DwStreamParams& p, uint8_t* obase, int oy, int oy_end, int ox0,
-                                           int32_t (&acc)[TX][4], const int4 bias) {
+                                           int32_t (&acc)[TX][4]) {
   if (oy >= 0 && oy < oy_end) {
     uint8_t* orow = obase + (size_t) oy * p.out_w * p.out_stride;
 #pragma unroll
     for (int x = 0; x < TX; x++) {
       if (ox0 + x < p.out_w) {
-        const uint32_t packed = pack_sat_u8x4(dws_requant<RQ>(acc[x][0], p.rq), dws_requant<RQ>(acc[x][1], p.rq),
-                                              dws_requant<RQ>(acc[x][2], p.rq), dws_requant<RQ>(acc[x][3], p.rq));
+        const uint32_t packed =
+            pack_sat_u8x4(requant_dev<RQ>(acc[x][0], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][1], p.rq, p.shift_mul),
+                          requant_dev<RQ>(acc[x][2], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][3], p.rq, p.shift_mul));
         *reinterpret_cast<uint32_t*>(orow + (size_t) (ox0 + x) * p.out_stride) = packed;
       }
     }
   }
-#pragma unroll
-  for (int x = 0; x < TX; x++) acc[x][0] = bias.x, acc[x][1] = bias.y, acc[x][2] = bias.z, acc[x][3] = bias.w;
 }
 
 template <int S, int WMODE, int RQ>
-__global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __grid_constant__ DwStreamParams p) {
+__global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __grid_constant__ DwStreamParams p) {
   const long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.total_threads) return;
   const int cg = (int) (idx % p.cgroups);
@@ -206,10 +189,13 @@ __global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __gri
         if (t < T) {
           uint32_t win[TX][4];
           row_windows<1>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, win);
-#pragma unroll
-          for (int ky = 0; ky < 3; ky++) accumulate_row<WMODE>(win, wa[ky], wb[ky], acc[(v - ky + 3) % 3]);
-          // (contributions to rows o < 0 land in slots that are reset below before their first real use)
-          finish_row<RQ>(p, obase, oy0 + t - 2 < oy0 ? -1 : oy0 + t - 2, oy_end, ox0, acc[(v + 1) % 3], bias);
+          // kernel row 0 opens output row t (its slot restarts from the bias); rows 1, 2 continue rows t-1, t-2.
+          // (For t < 2 the "continued" rows do not exist: their slots collect garbage that is overwritten by the
+          //  next INIT before it could ever be stored.)
+          accumulate_row<WMODE, true>(win, wa[0], wb[0], acc[v], bias);
+          accumulate_row<WMODE, false>(win, wa[1], wb[1], acc[(v + 2) % 3], bias);
+          accumulate_row<WMODE, false>(win, wa[2], wb[2], acc[(v + 1) % 3], bias);
+          finish_row<RQ>(p, obase, t < 2 ? -1 : oy0 + t - 2, oy_end, ox0, acc[(v + 1) % 3]);
         }
       }
     }
@@ -228,12 +214,12 @@ __global__ void __launch_bounds__(128, 4) q8_dwconv3x3_stream_kernel(const __gri
           uint32_t win[TX][4];
           row_windows<2>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, win);
           if ((v & 1) == 0) {
-            accumulate_row<WMODE>(win, wa[0], wb[0], acc[v >> 1]);
-            accumulate_row<WMODE>(win, wa[2], wb[2], acc[1 - (v >> 1)]);
+            accumulate_row<WMODE, true>(win, wa[0], wb[0], acc[v >> 1], bias);
+            accumulate_row<WMODE, false>(win, wa[2], wb[2], acc[1 - (v >> 1)], bias);
             const int o = (t >> 1) - 1;
-            finish_row<RQ>(p, obase, o < 0 ? -1 : oy0 + o, oy_end, ox0, acc[1 - (v >> 1)], bias);
+            finish_row<RQ>(p, obase, o < 0 ? -1 : oy0 + o, oy_end, ox0, acc[1 - (v >> 1)]);
           } else {
-            accumulate_row<WMODE>(win, wa[1], wb[1], acc[v >> 1]);
+            accumulate_row<WMODE, false>(win, wa[1], wb[1], acc[v >> 1], bias);
           }
         }
       }

@@ -29,6 +29,7 @@
 #include <string.h>
 
 #include "q8_igemm_sm100.cuh"
+#include "requant_dev.cuh"
 #include "sm100_ptx.cuh"
 
 namespace q8 {
@@ -293,34 +294,6 @@ __device__ __forceinline__ void copy_bytes16(uint32_t dst, const uint8_t* src, i
 // ------------------------------------------------------------------------------------------------
 // epilogue
 // ------------------------------------------------------------------------------------------------
-// Requantise one accumulator (requant_math.h has the derivation and the host-checked reference forms).
-// RQ 0/1: fused form, shift in [2,23]:  y = hi32(n*mult + {c_hi, c_lo | sign(n)}) + (n >> 31)  >> (shift-1)
-//         = LOP3 + IMAD.HI + LEA.HI + SHF per value (+ 1/2 I2IP for the saturating pack).
-template <int RQ>
-__device__ __forceinline__ int32_t requant_dev(int32_t n, const IgemmParams& p) {
-  if constexpr (RQ == 0 || RQ == 1) {
-    const uint32_t lo = (uint32_t) p.rq.c_pos | ((uint32_t) n & 0x80000000u);
-    const int64_t addend = (int64_t) (((uint64_t) (uint32_t) (p.rq.c_pos >> 32) << 32) | lo);
-    const int32_t hi = (int32_t) (((int64_t) n * (int64_t) p.rq.multiplier + addend) >> 32);
-    // final arithmetic shift by (shift-1): as a multiply-high by 2^(33-shift) it runs on the FMA pipe and
-    // leaves the (busier) ALU pipe to LOP3 / LEA / I2IP
-    int32_t y = p.shift_mul != 0 ? __mulhi(hi + (n >> 31), p.shift_mul) : ((hi + (n >> 31)) >> (p.rq.shift - 1));
-    if constexpr (RQ == 1) {
-      y = max(y, p.rq.qmin);
-      y = min(y, p.rq.qmax);
-    }
-    return y;
-  } else if constexpr (RQ == 2) {
-    return q8_requant_shift0(n, p.rq.multiplier, p.rq.zero_point, p.rq.qmin, p.rq.qmax);
-  } else if constexpr (RQ == 4) {
-    int32_t y = q8_requant_fused_shift1_unclamped(n, p.rq.multiplier, p.rq.c_neg);
-    y = max(y, p.rq.qmin);
-    return min(y, p.rq.qmax);
-  } else {
-    return q8_requant_exact_slow(n, p.rq);
-  }
-}
-
 // Slow path of the direct store: fewer than 16 valid bytes, or a destination that is not 16-byte aligned.
 __device__ __noinline__ void store_row_partial(uint8_t* dst, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int valid,
                                                int vec) {
@@ -433,8 +406,8 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
   uint32_t w[W / 4];
 #pragma unroll
   for (int t = 0; t < W / 4; t++)
-    w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p), requant_dev<RQ>(v[4 * t + 1], p), requant_dev<RQ>(v[4 * t + 2], p),
-                         requant_dev<RQ>(v[4 * t + 3], p));  // saturation to [0,255] is the clamp when qmin=0,qmax=255
+    w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 1], p.rq, p.shift_mul),
+                         requant_dev<RQ>(v[4 * t + 2], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 3], p.rq, p.shift_mul));  // saturation to [0,255] is the clamp when qmin=0,qmax=255
   emit<W>(p, it, e, j, c0, w);
 }
 
@@ -511,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const long long first = blockIdx.x, step = gridDim.x;
 
-  if (warp >= kLoadWarp0) {
+  if (warp >= kLoadWarp0 && warp < kStoreWarp) {
     // ===================================== loaders =====================================
     const int ltid = tid - kLoadWarp0 * 32;
     {

@@ -28,6 +28,7 @@
 #include "../../include/qnnpack_cuda.h"
 #include "q8_dwconv_sm100.cuh"
 #include "q8_igemm_sm100.cuh"
+#include "requant_dev.cuh"
 
 namespace q8 {
 cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, int grid, cudaStream_t stream);
@@ -560,7 +561,7 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       ov = pow2_align((uintptr_t) op->out_stride, ov);
       if (op->groups > 1) ov = pow2_align((uintptr_t) op->goc, ov);  // group offset g*goc (tile offsets are multiples of 16)
       p.out_vec = ov;
-      p.shift_mul = (op->rq.fused && op->rq.shift >= 3) ? (int) (1u << (33 - op->rq.shift)) : 0;
+      p.shift_mul = q8::requant_shift_mul(op->rq);
       // loader vector width
       int vec = pow2_align((uintptr_t) in, 16);
       vec = pow2_align((uintptr_t) op->in_stride, vec);
@@ -612,7 +613,7 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         sp.in_h = (int) op->in_h, sp.in_w = (int) op->in_w, sp.out_h = (int) op->out_h, sp.out_w = (int) op->out_w;
         sp.stride = (int) op->stride_h, sp.pad_top = (int) op->pad_top, sp.pad_left = (int) op->pad_left;
         sp.wmode = op->dw_wmode, sp.izp = op->izp;
-        sp.rq = op->rq, sp.rq_mode = op->rq_mode;
+        sp.rq = op->rq, sp.rq_mode = op->rq_mode, sp.shift_mul = q8::requant_shift_mul(op->rq);
         e = q8::launch_q8_dwconv3x3_stream(sp, stream);
       } else {
         e = q8::launch_q8_dwconv3x3(p, cv == 4 ? 4 : 1, stream);

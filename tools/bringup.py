@@ -76,16 +76,16 @@ np.savez_compressed(os.path.join(%(out)r, "igemm_dump_%(M)d_%(K)d_%(N)d.npz"), a
 
 STEPS = [
     ("env", "import torch; print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0)); "
-            "import subprocess; print(subprocess.run(['nvidia-smi'], capture_output=True, text=True).stdout[:1500])", 120),
-    ("igemm 128x32x16 nozp", dict(M=128, K=32, N=16, izp=0, kzp=0, oscale=40000.0), 120),
-    ("igemm 128x32x16 kzp128", dict(M=128, K=32, N=16, izp=0, kzp=128, oscale=40000.0), 120),
-    ("igemm 200x24x144", dict(M=200, K=24, N=144, izp=9, kzp=255, oscale=40000.0), 120),
-    ("igemm 128x32x16 zp", dict(M=128, K=32, N=16, izp=7, kzp=5, oscale=40000.0), 120),
-    ("igemm 300x144x24", dict(M=300, K=144, N=24, izp=7, kzp=5, oscale=90000.0), 120),
-    ("igemm 1000x64x384", dict(M=1000, K=64, N=384, izp=127, kzp=127, oscale=400.0), 120),
-    ("igemm 700x1280x1000", dict(M=700, K=1280, N=1000, izp=127, kzp=127, oscale=2000.0), 120),
-    ("igemm 5000x32x16", dict(M=5000, K=32, N=16, izp=3, kzp=200, oscale=40000.0), 120),
-    ("igemm 3000x192x32", dict(M=3000, K=192, N=32, izp=127, kzp=127, oscale=900.0), 120),
+            "import subprocess; print(subprocess.run(['nvidia-smi'], capture_output=True, text=True).stdout[:1500])", 45),
+    ("igemm 128x32x16 nozp", dict(M=128, K=32, N=16, izp=0, kzp=0, oscale=40000.0), 45),
+    ("igemm 128x32x16 kzp128", dict(M=128, K=32, N=16, izp=0, kzp=128, oscale=40000.0), 45),
+    ("igemm 200x24x144", dict(M=200, K=24, N=144, izp=9, kzp=255, oscale=40000.0), 45),
+    ("igemm 128x32x16 zp", dict(M=128, K=32, N=16, izp=7, kzp=5, oscale=40000.0), 45),
+    ("igemm 300x144x24", dict(M=300, K=144, N=24, izp=7, kzp=5, oscale=90000.0), 45),
+    ("igemm 1000x64x384", dict(M=1000, K=64, N=384, izp=127, kzp=127, oscale=400.0), 45),
+    ("igemm 700x1280x1000", dict(M=700, K=1280, N=1000, izp=127, kzp=127, oscale=2000.0), 45),
+    ("igemm 5000x32x16", dict(M=5000, K=32, N=16, izp=3, kzp=200, oscale=40000.0), 45),
+    ("igemm 3000x192x32", dict(M=3000, K=192, N=32, izp=127, kzp=127, oscale=900.0), 45),
 ]
 
 
