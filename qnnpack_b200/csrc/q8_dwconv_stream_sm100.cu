@@ -50,15 +50,14 @@ __device__ __forceinline__ void transpose4(uint32_t a, uint32_t b, uint32_t c, u
   t[3] = __byte_perm(ab_hi, cd_hi, 0x7632);
 }
 
-// Windows of one input row: win[x][c] = bytes (pixel x*S + 0, +1, +2, <don't care>) of channel c.
+// Load the NC = (TX-1)*S + 3 input pixels (4 channels each) one input row contributes to this thread's strip.
 // rp = address of (row iy, column ix0) — may lie outside the image for padded rows/columns, in which case it is
 // never dereferenced; colmask bit j = column ix0 + j is inside the image.
 template <int S>
-__device__ __forceinline__ void row_windows(const uint8_t* rp, const int (&coff)[(TX - 1) * S + 3], bool rowok, uint32_t colmask,
-                                            uint32_t fill, uint32_t (&win)[TX][4]) {
+__device__ __forceinline__ void load_cols(const uint8_t* rp, const int (&coff)[(TX - 1) * S + 3], bool rowok, uint32_t colmask,
+                                          uint32_t fill, uint32_t (&col)[(TX - 1) * S + 3]) {
   constexpr int NC = (TX - 1) * S + 3;
   constexpr uint32_t kAll = (1u << NC) - 1;
-  uint32_t col[NC];
   if (rowok && colmask == kAll) {
 #pragma unroll
     for (int j = 0; j < NC; j++) col[j] = __ldg(reinterpret_cast<const uint32_t*>(rp + coff[j]));
@@ -67,6 +66,11 @@ __device__ __forceinline__ void row_windows(const uint8_t* rp, const int (&coff)
     for (int j = 0; j < NC; j++)
       col[j] = (rowok && ((colmask >> j) & 1u)) ? __ldg(reinterpret_cast<const uint32_t*>(rp + coff[j])) : fill;
   }
+}
+
+// Windows of one input row: win[x][c] = bytes (pixel x*S + 0, +1, +2, <don't care>) of channel c.
+template <int S>
+__device__ __forceinline__ void build_windows(const uint32_t (&col)[(TX - 1) * S + 3], uint32_t (&win)[TX][4]) {
   uint32_t t0[4];
   transpose4(col[0], col[1], col[2], col[3], t0);
   if constexpr (S == 1) {
@@ -94,7 +98,6 @@ __device__ __forceinline__ void row_windows(const uint8_t* rp, const int (&coff)
   }
 }
 
-// WMODE 0: one s8 operand; 1: one u8 operand (kzp == 0); 2: two s8 operands (w - kzp = A + B)
 // INIT: this is the first kernel row of a new output row -> start from the folded bias instead of accumulating
 template <int WMODE, bool INIT>
 __device__ __forceinline__ void accumulate_row(const uint32_t (&win)[TX][4], const uint32_t (&wa)[4], const uint32_t (&wb)[4],
@@ -182,13 +185,20 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
     for (int s = 0; s < 3; s++)
 #pragma unroll
       for (int x = 0; x < TX; x++) acc[s][x][0] = bias.x, acc[s][x][1] = bias.y, acc[s][x][2] = bias.z, acc[s][x][3] = bias.w;
+    uint32_t col[NC], nxt[NC];  // the current input row and the prefetched next one (loads overlap the dp4a work)
+    load_cols<1>(rp, coff, (unsigned) iy0 < (unsigned) p.in_h, colmask, fill, col);
     for (int t3 = 0; t3 < T; t3 += 3) {
 #pragma unroll
       for (int v = 0; v < 3; v++) {
         const int t = t3 + v;
         if (t < T) {
+          if (t + 1 < T) {
+            load_cols<1>(rp + (long long) (t + 1) * row_pitch, coff, (unsigned) (iy0 + t + 1) < (unsigned) p.in_h, colmask, fill, nxt);
+          }
           uint32_t win[TX][4];
-          row_windows<1>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, win);
+          build_windows<1>(col, win);
+#pragma unroll
+          for (int j = 0; j < NC; j++) col[j] = nxt[j];
           // kernel row 0 opens output row t (its slot restarts from the bias); rows 1, 2 continue rows t-1, t-2.
           // (For t < 2 the "continued" rows do not exist: their slots collect garbage that is overwritten by the
           //  next INIT before it could ever be stored.)
@@ -206,13 +216,20 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
     for (int s = 0; s < 2; s++)
 #pragma unroll
       for (int x = 0; x < TX; x++) acc[s][x][0] = bias.x, acc[s][x][1] = bias.y, acc[s][x][2] = bias.z, acc[s][x][3] = bias.w;
+    uint32_t col[NC], nxt[NC];
+    load_cols<2>(rp, coff, (unsigned) iy0 < (unsigned) p.in_h, colmask, fill, col);
     for (int t4 = 0; t4 < T; t4 += 4) {
 #pragma unroll
       for (int v = 0; v < 4; v++) {
         const int t = t4 + v;
         if (t < T) {
+          if (t + 1 < T) {
+            load_cols<2>(rp + (long long) (t + 1) * row_pitch, coff, (unsigned) (iy0 + t + 1) < (unsigned) p.in_h, colmask, fill, nxt);
+          }
           uint32_t win[TX][4];
-          row_windows<2>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, win);
+          build_windows<2>(col, win);
+#pragma unroll
+          for (int j = 0; j < NC; j++) col[j] = nxt[j];
           if ((v & 1) == 0) {
             accumulate_row<WMODE, true>(win, wa[0], wb[0], acc[v >> 1], bias);
             accumulate_row<WMODE, false>(win, wa[2], wb[2], acc[1 - (v >> 1)], bias);

@@ -577,27 +577,29 @@ __global__ void __launch_bounds__(kThreads, 1)
           int cs = p.nkc - ks * p.skc;
           cs = cs < p.skc ? cs : p.skc;
           const uint32_t b_base = p.b_resident ? blk + (uint32_t) (ks * p.skc) * b_lbo : a_stage + p.mt * sub_bytes;
-          for (int j = 0; j < it.mt_eff; j++) {
-            const uint32_t d = d_tmem + j * p.n_mma;
-            uint32_t acc = ks != 0 ? 1u : 0u;
-            if (p.folded && ks == 0) {
-              // accumulator := folded bias  (A = [255 x31, 1] in every row, B = signed base-255 digits)
-              for (int t = 0; t < p.bias_steps; t++) {
-                umma_i8(d, umma_desc_kmajor_noswizzle(a_const, kChunkBytes, 128),
-                        umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo, b_lbo, 128), idesc_us, acc);
-                acc = 1u;
-              }
+          // UMMAs that accumulate into the same TMEM columns serialise (each waits for the previous result), so
+          // the sub-tiles are the INNER loop: consecutive instructions hit different accumulators and pipeline.
+          if (p.folded && ks == 0) {
+            // accumulator := folded bias  (A = [255 x31, 1] in every row, B = signed base-255 digits)
+            for (int t = 0; t < p.bias_steps; t++) {
+              const uint64_t ad = umma_desc_kmajor_noswizzle(a_const, kChunkBytes, 128);
+              const uint64_t bd = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo, b_lbo, 128);
+              for (int j = 0; j < it.mt_eff; j++) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
             }
-            for (int c = 0; c < cs; c += 2) {
-              const uint64_t a_desc = umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128);
-              umma_i8(d, a_desc, umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128), idesc_main, acc);
-              acc = 1u;
-              if (p.has_b2) {
-                // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
-                const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
-                umma_i8(d, a_desc, umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo, b_lbo, 128),
-                        idesc_us, 1u);
-              }
+          }
+          for (int c = 0; c < cs; c += 2) {
+            const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
+            const uint64_t bd = umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128);
+            for (int j = 0; j < it.mt_eff; j++)
+              umma_i8(d_tmem + j * p.n_mma, umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128),
+                      bd, idesc_main, acc);
+            if (p.has_b2) {
+              // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
+              const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
+              const uint64_t b2 = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo, b_lbo, 128);
+              for (int j = 0; j < it.mt_eff; j++)
+                umma_i8(d_tmem + j * p.n_mma,
+                        umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128), b2, idesc_us, 1u);
             }
           }
           umma_commit(smem_u32(&ctl.empty[stage]));
