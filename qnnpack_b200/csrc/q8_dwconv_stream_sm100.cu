@@ -185,20 +185,15 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
     for (int s = 0; s < 3; s++)
 #pragma unroll
       for (int x = 0; x < TX; x++) acc[s][x][0] = bias.x, acc[s][x][1] = bias.y, acc[s][x][2] = bias.z, acc[s][x][3] = bias.w;
-    uint32_t col[NC], nxt[NC];  // the current input row and the prefetched next one (loads overlap the dp4a work)
-    load_cols<1>(rp, coff, (unsigned) iy0 < (unsigned) p.in_h, colmask, fill, col);
     for (int t3 = 0; t3 < T; t3 += 3) {
 #pragma unroll
       for (int v = 0; v < 3; v++) {
         const int t = t3 + v;
         if (t < T) {
-          if (t + 1 < T) {
-            load_cols<1>(rp + (long long) (t + 1) * row_pitch, coff, (unsigned) (iy0 + t + 1) < (unsigned) p.in_h, colmask, fill, nxt);
-          }
+          uint32_t col[NC];
+          load_cols<1>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, col);
           uint32_t win[TX][4];
           build_windows<1>(col, win);
-#pragma unroll
-          for (int j = 0; j < NC; j++) col[j] = nxt[j];
           // kernel row 0 opens output row t (its slot restarts from the bias); rows 1, 2 continue rows t-1, t-2.
           // (For t < 2 the "continued" rows do not exist: their slots collect garbage that is overwritten by the
           //  next INIT before it could ever be stored.)
@@ -216,20 +211,15 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
     for (int s = 0; s < 2; s++)
 #pragma unroll
       for (int x = 0; x < TX; x++) acc[s][x][0] = bias.x, acc[s][x][1] = bias.y, acc[s][x][2] = bias.z, acc[s][x][3] = bias.w;
-    uint32_t col[NC], nxt[NC];
-    load_cols<2>(rp, coff, (unsigned) iy0 < (unsigned) p.in_h, colmask, fill, col);
     for (int t4 = 0; t4 < T; t4 += 4) {
 #pragma unroll
       for (int v = 0; v < 4; v++) {
         const int t = t4 + v;
         if (t < T) {
-          if (t + 1 < T) {
-            load_cols<2>(rp + (long long) (t + 1) * row_pitch, coff, (unsigned) (iy0 + t + 1) < (unsigned) p.in_h, colmask, fill, nxt);
-          }
+          uint32_t col[NC];
+          load_cols<2>(rp + (long long) t * row_pitch, coff, (unsigned) (iy0 + t) < (unsigned) p.in_h, colmask, fill, col);
           uint32_t win[TX][4];
           build_windows<2>(col, win);
-#pragma unroll
-          for (int j = 0; j < NC; j++) col[j] = nxt[j];
           if ((v & 1) == 0) {
             accumulate_row<WMODE, true>(win, wa[0], wb[0], acc[v >> 1], bias);
             accumulate_row<WMODE, false>(win, wa[2], wb[2], acc[1 - (v >> 1)], bias);

@@ -48,8 +48,8 @@ constexpr int kTmemCols = 512;
 struct __align__(8) SmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[kMaxAccStages];
+  uint64_t tmem_empty[kMaxAccStages];
   uint64_t b_full;
   uint64_t out_full[2];  // epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
   uint64_t out_free[2];  // store thread -> epilogue pair: the staging buffer may be overwritten
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(smem_u32(&ctl.full[s]), VEC == kVecTma ? (p.b_resident ? 1 : 1 + kLoadThreads) : kLoadThreads);
       mbar_init(smem_u32(&ctl.empty[s]), 1);
     }
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < kMaxAccStages; s++) {
       mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
       mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiPairThreads);
     }
@@ -563,10 +563,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       long long li = 0;
       for (long long item = first; item < p.total_items; item += step, li++) {
         const Item it = decode_item(p, item);
-        const int as = (int) (li & 1);
-        mbar_wait(smem_u32(&ctl.tmem_empty[as]), (uint32_t) ((li >> 1) & 1) ^ 1);
+        // accumulator stage of this item: round-robin over 2..4 TMEM stages, so the UMMAs of the next items run
+        // (and their ~100-cycle dependent-issue latency is paid) while the epilogue still drains earlier ones
+        const int as = (int) (li % p.acc_stages);
+        mbar_wait(smem_u32(&ctl.tmem_empty[as]), (uint32_t) ((li / p.acc_stages) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * kMaxNMma;
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         // base of this (group, n_tile)'s resident block: [B1: nkc][B2 full: 2][B2 tail: 2][bias digits: 2 per step]
         const uint32_t blk = b_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.blk_chunks) * b_lbo;
         for (int ks = 0; ks < p.k_stages; ks++) {
@@ -627,10 +629,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t k = (uint32_t) (li >> 1);  // this pair's item counter
       const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
       if (p.out_mode == 1) mbar_wait(smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1);  // staging buffer is free again
-      mbar_wait(smem_u32(&ctl.tmem_full[pair]), k & 1);
+      const int as = (int) (li % p.acc_stages);
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), (uint32_t) ((li / p.acc_stages) & 1));
       tc_fence_after_sync();
       EpiCtx e;
-      e.tlane = tmem_base + pair * kMaxNMma + ((uint32_t) (q * 32) << 16);
+      e.tlane = tmem_base + as * p.acc_stride + ((uint32_t) (q * 32) << 16);
       e.bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
       e.staging = staging;
       e.obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
@@ -647,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       // done reading the accumulator stage: the UMMA warp may reuse it once the pair's 8 warps have arrived
       tc_fence_before_sync();
-      mbar_arrive(smem_u32(&ctl.tmem_empty[pair]));
+      mbar_arrive(smem_u32(&ctl.tmem_empty[as]));
       if (p.out_mode == 1) {
         fence_proxy_async_smem();  // staging writes (generic proxy) -> bulk copy (async proxy)
         mbar_arrive(smem_u32(&ctl.out_full[pair]));

@@ -284,7 +284,10 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
   // subject to >= 3 ring stages and >= 64 KB of loads in flight (or the whole K of 3 items); weights stay
   // resident in smem when they fit beside that.
   const int smem_max = smem_optin - kCtlReserve - 1024;
-  int mt_max = q8::kMaxNMma / pl->n_mma;
+  // sub-tiles per item: mt * n_mma columns per accumulator stage; prefer >= 4 stages in the 512 TMEM columns
+  // (mt * n_mma <= 128) so that UMMA issue latency hides behind the epilogue, but never below 1 sub-tile
+  int mt_max = 128 / pl->n_mma;
+  if (mt_max < 1) mt_max = 1;
   if (mt_max > q8::kMaxSubTiles) mt_max = q8::kMaxSubTiles;
   if (mt_max < 1) mt_max = 1;
   if (const char* e = getenv("QNNP_CUDA_MAX_SUBTILES")) {
@@ -376,7 +379,12 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
     if (s > steps) steps = s;
   }
   const char* mode_env = getenv("QNNP_CUDA_IGEMM_MODE");
-  const bool want_folded = !(mode_env != nullptr && strcmp(mode_env, "ones") == 0) && steps <= kMaxBiasSteps;
+  // Folded mode removes two instructions per output from the (instruction-bound) epilogue at the price of 2-3x the
+  // UMMA count; measured on B200 it wins when the layer writes more than it reads (N > K) and loses on the narrow
+  // projection layers, where UMMA issue is the longer pole.  QNNP_CUDA_IGEMM_MODE=ones|folded overrides.
+  bool want_folded = steps <= kMaxBiasSteps && op->goc > K;
+  if (mode_env != nullptr && strcmp(mode_env, "ones") == 0) want_folded = false;
+  if (mode_env != nullptr && strcmp(mode_env, "folded") == 0) want_folded = steps <= kMaxBiasSteps;
   IgemmPlan pl;
   // folded mode only when its plan keeps a healthy ring; otherwise the "ones" plan (weights may stream)
   bool planned = want_folded && plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, 1, steps, &pl) && pl.good;
@@ -535,6 +543,13 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.M = (long long) M;
       p.m_tiles = (long long) ceil_div(M, q8::kTileM);
       p.m_super = (long long) ceil_div((size_t) p.m_tiles, (size_t) op->mt);
+      p.acc_stride = op->mt * op->n_mma;
+      p.acc_stages = 512 / p.acc_stride;
+      if (p.acc_stages > q8::kMaxAccStages) p.acc_stages = q8::kMaxAccStages;
+      if (const char* e = getenv("QNNP_CUDA_ACC_STAGES")) {
+        const int v = atoi(e);
+        if (v >= 2 && v <= p.acc_stages) p.acc_stages = v;
+      }
       p.total_items = (long long) op->groups * p.m_super * op->n_tiles;
       p.in_stride = (long long) op->in_stride;
       p.out_stride = (long long) op->out_stride;
