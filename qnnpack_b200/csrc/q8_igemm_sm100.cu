@@ -62,15 +62,27 @@ struct Item {
   int mt_eff;    // sub-tiles that contain at least one valid row
 };
 
-__device__ __forceinline__ Item decode_item(const IgemmParams& p, long long item) {
+// Work item -> (group, super-tile, n-tile).  Every role decodes every item, the single UMMA-issuing thread among
+// them, so this must be cheap: 32-bit arithmetic only (the host guarantees total_items, m_tiles < 2^31) and no
+// division at all in the common single-n-tile, single-group case.  (64-bit div/mod here cost ~1 us per item.)
+__device__ __forceinline__ Item decode_item(const IgemmParams& p, long long item64) {
+  const uint32_t item = (uint32_t) item64;
   Item it;
-  it.nt = (int) (item % p.n_tiles);
-  const long long rest = item / p.n_tiles;
-  const long long st = rest % p.m_super;
-  it.g = (int) (rest / p.m_super);
-  it.m0 = st * p.mt * kTileM;
-  const long long left = p.m_tiles - st * p.mt;
-  it.mt_eff = left < p.mt ? (int) left : p.mt;
+  uint32_t st;
+  if (p.n_tiles == 1 && p.groups == 1) {
+    it.nt = 0;
+    it.g = 0;
+    st = item;
+  } else {
+    const uint32_t n_tiles = (uint32_t) p.n_tiles, m_super = (uint32_t) p.m_super;
+    const uint32_t rest = item / n_tiles;
+    it.nt = (int) (item - rest * n_tiles);
+    it.g = (int) (rest / m_super);
+    st = rest - (uint32_t) it.g * m_super;
+  }
+  it.m0 = (long long) st * (p.mt * kTileM);
+  const uint32_t left = (uint32_t) p.m_tiles - st * (uint32_t) p.mt;
+  it.mt_eff = left < (uint32_t) p.mt ? (int) left : p.mt;
   return it;
 }
 
@@ -143,10 +155,11 @@ __device__ __forceinline__ void load_a_conv(const IgemmParams& p, const Item& it
   for (int j = 0; j < it.mt_eff; j++) {
     const long long m = it.m0 + (long long) j * kTileM + ltid;
     if (m < p.M) {  // (no early exit: every loader thread must still arrive on the stage barrier)
-      const int ox = (int) (m % p.out_w);
-      const long long t = m / p.out_w;
-      const int oy = (int) (t % p.out_h);
-      const long long n = t / p.out_h;
+      const uint32_t mu = (uint32_t) m;  // M < 2^31 (host-checked): 32-bit divisions only
+      const uint32_t t = mu / (uint32_t) p.out_w;
+      const int ox = (int) (mu - t * (uint32_t) p.out_w);
+      const uint32_t n = t / (uint32_t) p.out_h;
+      const int oy = (int) (t - n * (uint32_t) p.out_h);
       const int iy0 = oy * p.stride_h - p.pad_top, ix0 = ox * p.stride_w - p.pad_left;
       int c = c0, ky = ky0, kx = kx0;
       const uint32_t drow = a_stage + (uint32_t) (j * p.skc) * kChunkBytes + (uint32_t) ltid * 16;
@@ -188,21 +201,21 @@ __device__ __forceinline__ void run9_load(const uint8_t* src, uint32_t (&w)[3]) 
 }
 
 __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid) {
-  constexpr int NB = 2;  // pixels (sub-tiles) in flight per thread
+  constexpr int NB = 4;  // pixels (sub-tiles) in flight per thread
   const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
   for (int j0 = 0; j0 < it.mt_eff; j0 += NB) {
     uint32_t w[NB][3][3];
     // per run: bits 0-1 = byte alignment of the source, bits 2-3 = state (0: in bounds, 1: all padding, 2: edge)
-    uint32_t info[NB] = {0, 0};
+    uint32_t info[NB] = {};
 #pragma unroll
     for (int jj = 0; jj < NB; jj++) {
       const long long m = it.m0 + (long long) (j0 + jj) * kTileM + ltid;
       const bool live = (j0 + jj) < it.mt_eff && m < p.M;
-      const long long mm = live ? m : 0;
-      const int ox = (int) (mm % p.out_w);
-      const long long t = mm / p.out_w;
-      const int oy = (int) (t % p.out_h);
-      const long long n = t / p.out_h;
+      const uint32_t mu = live ? (uint32_t) m : 0u;  // M < 2^31 (host-checked): 32-bit divisions only
+      const uint32_t t = mu / (uint32_t) p.out_w;
+      const int ox = (int) (mu - t * (uint32_t) p.out_w);
+      const uint32_t n = t / (uint32_t) p.out_h;
+      const int oy = (int) (t - n * (uint32_t) p.out_h);
       const int iy0 = oy * p.stride_h - p.pad_top, ix0 = ox * p.stride_w - p.pad_left;
       const bool full = ix0 >= 0 && ix0 + p.kw <= p.in_w;
       const uint8_t* img = p.in + ((size_t) n * p.in_h * p.in_w + (full ? ix0 : 0)) * 3;
@@ -237,11 +250,11 @@ __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Ite
             r[ky][0] = fill, r[ky][1] = fill, r[ky][2] = fill & 0xFFu;
           } else {
             // left/right edge: assemble the run byte by byte (rare: one pixel per image row)
-            const long long m = it.m0 + (long long) (j0 + jj) * kTileM + ltid;
-            const int ox = (int) (m % p.out_w);
-            const long long t = m / p.out_w;
-            const int oy = (int) (t % p.out_h);
-            const long long n = t / p.out_h;
+            const uint32_t mu = (uint32_t) (it.m0 + (long long) (j0 + jj) * kTileM + ltid);
+            const uint32_t t = mu / (uint32_t) p.out_w;
+            const int ox = (int) (mu - t * (uint32_t) p.out_w);
+            const uint32_t n = t / (uint32_t) p.out_h;
+            const int oy = (int) (t - n * (uint32_t) p.out_h);
             const int ix0 = ox * p.stride_w - p.pad_left;
             const int iy = oy * p.stride_h - p.pad_top + ky * p.dil_h;
             const uint8_t* rowp = p.in + ((size_t) n * p.in_h + iy) * p.in_w * 3;
@@ -560,13 +573,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       int stage = 0;
       uint32_t phase = 0;
-      long long li = 0;
-      for (long long item = first; item < p.total_items; item += step, li++) {
+      int as = -1;             // accumulator stage of the item: round-robin over the 2..4 TMEM stages, so the UMMAs
+      uint32_t as_phase = 1;   // of the next items run while the epilogue still drains earlier ones
+      for (long long item = first; item < p.total_items; item += step) {
         const Item it = decode_item(p, item);
-        // accumulator stage of this item: round-robin over 2..4 TMEM stages, so the UMMAs of the next items run
-        // (and their ~100-cycle dependent-issue latency is paid) while the epilogue still drains earlier ones
-        const int as = (int) (li % p.acc_stages);
-        mbar_wait(smem_u32(&ctl.tmem_empty[as]), (uint32_t) ((li / p.acc_stages) & 1) ^ 1);
+        if (++as == p.acc_stages) as = 0;
+        as_phase ^= (as == 0);
+        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         // base of this (group, n_tile)'s resident block: [B1: nkc][B2 full: 2][B2 tail: 2][bias digits: 2 per step]
@@ -623,14 +636,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int lane = tid & 31;
     const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
     mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem ("ones" mode reads them)
-    long long li = pair;
-    for (long long item = first + pair * step; item < p.total_items; item += 2 * step, li += 2) {
+    int as = pair - 2;        // accumulator stage = (local item index) mod acc_stages, tracked without divisions
+    uint32_t as_phase = 0;    // = ((local item index) / acc_stages) & 1
+    uint32_t k = ~0u;         // this pair's item counter
+    for (long long item = first + pair * step; item < p.total_items; item += 2 * step) {
       const Item it = decode_item(p, item);
-      const uint32_t k = (uint32_t) (li >> 1);  // this pair's item counter
+      k++;
+      as += 2;
+      if (as >= p.acc_stages) {
+        as -= p.acc_stages;
+        as_phase ^= 1;
+      }
       const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
       if (p.out_mode == 1) mbar_wait(smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1);  // staging buffer is free again
-      const int as = (int) (li % p.acc_stages);
-      mbar_wait(smem_u32(&ctl.tmem_full[as]), (uint32_t) ((li / p.acc_stages) & 1));
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
       tc_fence_after_sync();
       EpiCtx e;
       e.tlane = tmem_base + as * p.acc_stride + ((uint32_t) (q * 32) << 16);

@@ -284,9 +284,9 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
   // subject to >= 3 ring stages and >= 64 KB of loads in flight (or the whole K of 3 items); weights stay
   // resident in smem when they fit beside that.
   const int smem_max = smem_optin - kCtlReserve - 1024;
-  // sub-tiles per item: mt * n_mma columns per accumulator stage; prefer >= 4 stages in the 512 TMEM columns
-  // (mt * n_mma <= 128) so that UMMA issue latency hides behind the epilogue, but never below 1 sub-tile
-  int mt_max = 128 / pl->n_mma;
+  // sub-tiles per item: mt * n_mma <= 256 columns (two accumulator stages always fit the 512 TMEM columns; up to four
+  // are used when the item is narrower).  Measured: larger items win — per-item hand-over costs dominate small ones.
+  int mt_max = q8::kMaxNMma / pl->n_mma;
   if (mt_max < 1) mt_max = 1;
   if (mt_max > q8::kMaxSubTiles) mt_max = q8::kMaxSubTiles;
   if (mt_max < 1) mt_max = 1;
@@ -551,6 +551,10 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         if (v >= 2 && v <= p.acc_stages) p.acc_stages = v;
       }
       p.total_items = (long long) op->groups * p.m_super * op->n_tiles;
+      if (M >= (1ull << 31) || p.total_items >= (1ll << 31)) {
+        log_error("operator too large for one launch (M = %zu rows)", M);
+        return qnnp_status_unsupported_parameter;
+      }
       p.in_stride = (long long) op->in_stride;
       p.out_stride = (long long) op->out_stride;
       p.groups = (int) op->groups, p.gic = (int) op->gic, p.goc = (int) op->goc;
