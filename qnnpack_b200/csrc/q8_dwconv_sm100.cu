@@ -29,6 +29,10 @@ __device__ __forceinline__ int32_t requant_one(int32_t n, const Q8Requant& rq) {
     int32_t t = q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
     t = max(t, rq.qmin);
     return min(t, rq.qmax);
+  } else if constexpr (RQ == 5 || RQ == 6) {
+    int32_t t = q8_requant_u_unclamped((uint32_t) n ^ 0x80000000u, rq.u_m2, rq.u_k2, rq.u_sm);
+    if constexpr (RQ == 6) t = min(max(t, rq.qmin), rq.qmax);
+    return t;
   } else if constexpr (RQ == 2) {
     return q8_requant_shift0(n, rq.multiplier, rq.zero_point, rq.qmin, rq.qmax);
   } else if constexpr (RQ == 4) {
@@ -152,6 +156,8 @@ static cudaError_t launch_dw_rq(const DwParams& p, cudaStream_t stream) {
     case 1: q8_dwconv3x3_kernel<CV, SW, TX, 1><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     case 2: q8_dwconv3x3_kernel<CV, SW, TX, 2><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     case 4: q8_dwconv3x3_kernel<CV, SW, TX, 4><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
+    case 5: q8_dwconv3x3_kernel<CV, SW, TX, 5><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
+    case 6: q8_dwconv3x3_kernel<CV, SW, TX, 6><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     default: q8_dwconv3x3_kernel<CV, SW, TX, 3><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
   }
   return cudaGetLastError();

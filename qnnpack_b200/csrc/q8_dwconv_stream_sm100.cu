@@ -121,9 +121,18 @@ __device__ __forceinline__ void finish_row(const DwStreamParams& p, uint8_t* oba
 #pragma unroll
     for (int x = 0; x < TX; x++) {
       if (ox0 + x < p.out_w) {
-        const uint32_t packed =
-            pack_sat_u8x4(requant_dev<RQ>(acc[x][0], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][1], p.rq, p.shift_mul),
-                          requant_dev<RQ>(acc[x][2], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][3], p.rq, p.shift_mul));
+        uint32_t packed;
+        if constexpr (RQ == 5 || RQ == 6) {
+          auto rq1 = [&](int32_t nu) -> int32_t {
+            int32_t y = q8_requant_u_unclamped((uint32_t) nu, p.rq.u_m2, p.rq.u_k2, p.rq.u_sm);
+            if constexpr (RQ == 6) y = min(max(y, p.rq.qmin), p.rq.qmax);
+            return y;
+          };
+          packed = pack_sat_u8x4(rq1(acc[x][0]), rq1(acc[x][1]), rq1(acc[x][2]), rq1(acc[x][3]));
+        } else {
+          packed = pack_sat_u8x4(requant_dev<RQ>(acc[x][0], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][1], p.rq, p.shift_mul),
+                                 requant_dev<RQ>(acc[x][2], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][3], p.rq, p.shift_mul));
+        }
         *reinterpret_cast<uint32_t*>(orow + (size_t) (ox0 + x) * p.out_stride) = packed;
       }
     }
@@ -158,7 +167,10 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
       wb[ky][0] = wb[ky][1] = wb[ky][2] = wb[ky][3] = 0;
     }
   }
-  const int4 bias = __ldg(reinterpret_cast<const int4*>(p.bias + c0));
+  int4 bias = __ldg(reinterpret_cast<const int4*>(p.bias + c0));
+  if constexpr (RQ == 5 || RQ == 6) {  // "U" requantisation consumes n + 2^31 (mod 2^32): the offset rides on the bias
+    bias.x ^= 0x80000000, bias.y ^= 0x80000000, bias.z ^= 0x80000000, bias.w ^= 0x80000000;
+  }
 
   uint8_t* obase = p.out + (size_t) n * p.out_h * p.out_w * p.out_stride + c0;
   const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
@@ -243,6 +255,8 @@ cudaError_t launch_rq(const DwStreamParams& p, cudaStream_t stream) {
     case 1: q8_dwconv3x3_stream_kernel<S, WMODE, 1><<<blocks, threads, 0, stream>>>(p); break;
     case 2: q8_dwconv3x3_stream_kernel<S, WMODE, 2><<<blocks, threads, 0, stream>>>(p); break;
     case 4: q8_dwconv3x3_stream_kernel<S, WMODE, 4><<<blocks, threads, 0, stream>>>(p); break;
+    case 5: q8_dwconv3x3_stream_kernel<S, WMODE, 5><<<blocks, threads, 0, stream>>>(p); break;
+    case 6: q8_dwconv3x3_stream_kernel<S, WMODE, 6><<<blocks, threads, 0, stream>>>(p); break;
     default: q8_dwconv3x3_stream_kernel<S, WMODE, 3><<<blocks, threads, 0, stream>>>(p); break;
   }
   return cudaGetLastError();

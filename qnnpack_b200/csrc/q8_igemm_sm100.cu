@@ -402,8 +402,9 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
     for (int i = 0; i < W; i++) d[c0 + i] = v[i];
     if (!FOLDED && c0 == 0 && p.has_corr) d[p.n_tile] = rowsum;
   }
+  constexpr bool kU = (RQ == 5 || RQ == 6);  // "U" requantisation takes n XOR 2^31, i.e. n + 2^31 (mod 2^32)
   if constexpr (!FOLDED) {
-    const int32_t corr = -p.kzp * rowsum;
+    const int32_t corr = (int32_t) ((uint32_t) (-p.kzp * rowsum) + (kU ? 0x80000000u : 0u));  // offset rides on the bias add
 #pragma unroll
     for (int t = 0; t < W / 4; t++) {
       int4 b;
@@ -417,10 +418,23 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
     }
   }
   uint32_t w[W / 4];
+  if constexpr (kU) {
+    const uint32_t m2 = p.rq.u_m2, flip = FOLDED ? 0x80000000u : 0u;
+    const uint64_t k2 = p.rq.u_k2;
+    const int32_t sm = p.rq.u_sm;
+    auto rq1 = [&](int32_t n) -> int32_t {
+      int32_t y = q8_requant_u_unclamped((uint32_t) n ^ flip, m2, k2, sm);
+      if constexpr (RQ == 6) y = min(max(y, p.rq.qmin), p.rq.qmax);
+      return y;
+    };
 #pragma unroll
-  for (int t = 0; t < W / 4; t++)
-    w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 1], p.rq, p.shift_mul),
-                         requant_dev<RQ>(v[4 * t + 2], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 3], p.rq, p.shift_mul));  // saturation to [0,255] is the clamp when qmin=0,qmax=255
+    for (int t = 0; t < W / 4; t++) w[t] = pack_sat_u8x4(rq1(v[4 * t]), rq1(v[4 * t + 1]), rq1(v[4 * t + 2]), rq1(v[4 * t + 3]));
+  } else {
+#pragma unroll
+    for (int t = 0; t < W / 4; t++)  // (saturation to [0,255] is the clamp when qmin = 0, qmax = 255)
+      w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 1], p.rq, p.shift_mul),
+                           requant_dev<RQ>(v[4 * t + 2], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 3], p.rq, p.shift_mul));
+  }
   emit<W>(p, it, e, j, c0, w);
 }
 
@@ -665,6 +679,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         case 1: epilogue_dispatch<1>(p, it, e, half); break;
         case 2: epilogue_dispatch<2>(p, it, e, half); break;
         case 4: epilogue_dispatch<4>(p, it, e, half); break;
+        case 5: epilogue_dispatch<5>(p, it, e, half); break;
+        case 6: epilogue_dispatch<6>(p, it, e, half); break;
         default: epilogue_dispatch<3>(p, it, e, half); break;
       }
       // done reading the accumulator stage: the UMMA warp may reuse it once the pair's 8 warps have arrived

@@ -221,6 +221,18 @@ void free_operator(qnnp_operator* op) {
 
 int select_rq_mode(const Q8Requant& rq) { return q8_requant_mode(rq); }
 
+// Every accumulator of the operator obeys |n| <= max|bias| + K * 255 * 255 (n = bias + sum (a - izp)(w - kzp)); with
+// that bound the cheapest exact requantisation form ("U", requant_math.h) can be proven safe at create time.
+void enable_bounded_requant(qnnp_operator* op, const int32_t* bias, size_t count, size_t K) {
+  if (getenv("QNNP_CUDA_NO_URQ") != nullptr) return;
+  int64_t bmax = 0;
+  for (size_t i = 0; i < count; i++) {
+    const int64_t b = bias[i] < 0 ? -(int64_t) bias[i] : (int64_t) bias[i];
+    bmax = b > bmax ? b : bmax;
+  }
+  q8_requant_enable_u(op->rq, bmax + (int64_t) K * 255 * 255);
+}
+
 bool scale_ok(float s) { return s > 0.0f && isnormal(s); }
 
 uint32_t f32_bits(float f) {
@@ -798,6 +810,7 @@ QNNP_EXPORT enum qnnp_status qnnp_create_convolution2d_nhwc_q8(
   op->groups = groups, op->gic = group_input_channels, op->goc = group_output_channels;
   op->izp = input_zero_point, op->kzp = kernel_zero_point;
   op->rq = q8_make_requant(f32_bits(convolution_scale), output_zero_point, output_min, output_max);
+  enable_bounded_requant(op, bias, groups * group_output_channels, (size_t) kernel_height * kernel_width * group_input_channels);
   op->rq_mode = select_rq_mode(op->rq);
 
   // kernel family (reference: src/convolution.c:180-189)
@@ -877,6 +890,7 @@ QNNP_EXPORT enum qnnp_status qnnp_create_fully_connected_nc_q8(
   op->groups = 1, op->gic = input_channels, op->goc = output_channels;
   op->izp = input_zero_point, op->kzp = kernel_zero_point;
   op->rq = q8_make_requant(f32_bits(requantization_scale), output_zero_point, output_min, output_max);
+  enable_bounded_requant(op, bias, output_channels, input_channels);
   op->rq_mode = select_rq_mode(op->rq);
   op->kind = kKindIgemmGemm;
   enum qnnp_status st = plan_and_pack_igemm(op, kernel, bias);

@@ -10,6 +10,7 @@ namespace q8 {
 //         written so that the compiler emits LOP3 + IMAD.HI (64-bit addend pair) + LEA.HI + shift per value;
 //         the shift runs as a multiply-high (FMA pipe) when shift_mul = 2^(33-shift) != 0.
 //    2  : shift == 0      3: exact slow form (shift > 23)      4: fused, shift == 1
+//    5/6: "U" form (requant_math.h): XOR + IMAD.WIDE.U32 (constant addend) + LEA.HI + IMAD.HI; 6 adds the clamp
 // RQ 0 relies on the caller's u8-saturating pack for the clamp (qmin = 0, qmax = 255).
 template <int RQ>
 __device__ __forceinline__ int32_t requant_dev(int32_t n, const Q8Requant& rq, int32_t shift_mul) {
@@ -19,6 +20,13 @@ __device__ __forceinline__ int32_t requant_dev(int32_t n, const Q8Requant& rq, i
     const int32_t hi = (int32_t) (((int64_t) n * (int64_t) rq.multiplier + addend) >> 32);
     int32_t y = shift_mul != 0 ? __mulhi(hi + (n >> 31), shift_mul) : ((hi + (n >> 31)) >> (rq.shift - 1));
     if constexpr (RQ == 1) {
+      y = max(y, rq.qmin);
+      y = min(y, rq.qmax);
+    }
+    return y;
+  } else if constexpr (RQ == 5 || RQ == 6) {
+    int32_t y = q8_requant_u_unclamped((uint32_t) n ^ 0x80000000u, rq.u_m2, rq.u_k2, rq.u_sm);
+    if constexpr (RQ == 6) {
       y = max(y, rq.qmin);
       y = min(y, rq.qmax);
     }

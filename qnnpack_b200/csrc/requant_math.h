@@ -41,7 +41,10 @@ struct Q8Requant {
   int64_t c_pos;       // fused addends (valid when shift <= 23)
   int64_t c_neg;
   int32_t fused;       // 1 if the fused form may be used
-  int32_t pad_;
+  int32_t u_ok;        // 1 if the "U" form below may be used (needs a bound on |n|, see q8_requant_enable_u)
+  uint32_t u_m2;       // 2 * multiplier
+  int32_t u_sm;        // 2^(32 - shift): the final arithmetic shift as a multiply-high
+  uint64_t u_k2;       // 2*c_pos - 2^32*multiplier - 2^32   (mod 2^64)
 };
 
 // Host-side parameter derivation from the fp32 scale's bit pattern (requantization.h:131-141).
@@ -60,8 +63,42 @@ Q8_HD Q8Requant q8_make_requant(uint32_t scale_bits, uint8_t zero_point, uint8_t
     r.c_pos = (int64_t(1) << 30) + (s > 0 ? (int64_t(1) << (30 + s)) : 0) + (int64_t(zero_point) << (31 + s));
     r.c_neg = r.c_pos - (s > 0 ? (int64_t(1) << 31) : 0);
   }
-  r.pad_ = 0;
+  r.u_ok = 0;
+  r.u_m2 = 0;
+  r.u_sm = 0;
+  r.u_k2 = 0;
   return r;
+}
+
+// "U" form: the cheapest exact evaluation (4 integer instructions per value on the GPU: XOR, IMAD.WIDE.U32 with a
+// CONSTANT 64-bit addend, LEA.HI, IMAD.HI), available when the kernel can bound its accumulators, |n| <= nmax.
+//   X = n*mult + c_pos - [n<0]*2^31 is what the fused form shifts right by 31+s.  Write n = nu - 2^31 with
+//   nu = n XOR 2^31 (unsigned) and b = nu >> 31 = [n >= 0]:
+//       2X = nu*(2 mult) + b*2^32 + K2,     K2 = 2 c_pos - 2^32 mult - 2^32
+//       floor(X / 2^31) = hi32(nu*(2 mult) + K2) + b          (b*2^32 is a multiple of 2^32; K2 taken mod 2^64)
+//       out = floor(X / 2^31) >> s  =  mulhi(floor(X / 2^31), 2^(32-s))          for s >= 2
+//   The sign-dependent rounding term became the carry-free "+ b", and the 64-bit addend no longer depends on n.
+//   hi32 is taken modulo 2^32, which is exact when floor(X / 2^31) fits in int32 — guaranteed by the nmax check.
+Q8_HD void q8_requant_enable_u(Q8Requant& r, int64_t nmax) {
+  r.u_ok = 0;
+  if (!r.fused || r.shift < 2 || nmax < 0 || nmax > 0x7FFFFFFFll) return;
+  const int64_t bound = ((nmax * (int64_t) r.multiplier) >> 31) + (r.c_pos >> 31) + 2;
+  if (bound >= 0x7FFFFFFFll) return;
+  r.u_m2 = (uint32_t) r.multiplier << 1;
+  r.u_sm = (int32_t) (1u << (32 - r.shift));
+  r.u_k2 = 2ull * (uint64_t) r.c_pos - ((uint64_t) (uint32_t) r.multiplier << 32) - (1ull << 32);
+  r.u_ok = 1;
+}
+
+// nu = n XOR 0x80000000.  Returns y + zero_point, unclamped.
+Q8_HD int32_t q8_requant_u_unclamped(uint32_t nu, uint32_t m2, uint64_t k2, int32_t sm) {
+  const uint32_t hi = (uint32_t) (((uint64_t) nu * m2 + k2) >> 32);
+  const int32_t t = (int32_t) (hi + (nu >> 31));
+#if defined(__CUDA_ARCH__)
+  return __mulhi(t, sm);
+#else
+  return (int32_t) (((int64_t) t * (int64_t) sm) >> 32);
+#endif
 }
 
 // Straight transcription of the specification; used for shift > 23 and as the in-library cross-check.
@@ -116,9 +153,11 @@ Q8_HD int32_t q8_requant_shift0(int32_t n, int32_t multiplier, int32_t zero_poin
 }
 
 // 0: fused shift in [2,23], clamp provided by the u8 saturating pack; 1: same + explicit clamp;
-// 2: shift == 0; 3: exact slow form (shift > 23); 4: fused shift == 1
+// 2: shift == 0; 3: exact slow form (shift > 23); 4: fused shift == 1;
+// 5: "U" form, clamp provided by the u8 saturating pack; 6: "U" form + explicit clamp
 Q8_HD int q8_requant_mode(const Q8Requant& p) {
   if (!p.fused) return 3;
+  if (p.u_ok) return (p.qmin == 0 && p.qmax == 255) ? 5 : 6;
   if (p.shift == 0) return 2;
   if (p.shift == 1) return 4;
   return (p.qmin == 0 && p.qmax == 255) ? 0 : 1;
@@ -127,7 +166,7 @@ Q8_HD int q8_requant_mode(const Q8Requant& p) {
 Q8_HD int32_t q8_requant(int32_t n, const Q8Requant& p) {
   if (!p.fused) return q8_requant_exact_slow(n, p);
   if (p.shift == 0) return q8_requant_shift0(n, p.multiplier, p.zero_point, p.qmin, p.qmax);
-  int32_t y = p.shift == 1 ? q8_requant_fused_shift1_unclamped(n, p.multiplier, p.c_neg)
+  int32_t y = p.u_ok ? q8_requant_u_unclamped((uint32_t) n ^ 0x80000000u, p.u_m2, p.u_k2, p.u_sm) : p.shift == 1 ? q8_requant_fused_shift1_unclamped(n, p.multiplier, p.c_neg)
                            : q8_requant_fused_unclamped(n, p.multiplier, p.c_pos, p.shift - 1);
   y = y < p.qmin ? p.qmin : y;
   y = y > p.qmax ? p.qmax : y;

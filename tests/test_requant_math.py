@@ -20,8 +20,18 @@ extern "C" void hc_requant(size_t n, const int32_t* in, float scale, unsigned ch
                            unsigned char qmax, unsigned char* out, int force_slow) {
   uint32_t bits; memcpy(&bits, &scale, 4);
   Q8Requant p = q8_make_requant(bits, zp, qmin, qmax);
-  if (force_slow) p.fused = 0;
+  if (force_slow == 1) p.fused = 0;
   for (size_t i = 0; i < n; i++) out[i] = (unsigned char) q8_requant(in[i], p);
+}
+// the "U" form with the accumulator bound nmax; returns 0 (and leaves `out` alone) when the bound makes it ineligible
+extern "C" int hc_requant_u(size_t n, const int32_t* in, float scale, unsigned char zp, unsigned char qmin,
+                            unsigned char qmax, unsigned char* out, long long nmax) {
+  uint32_t bits; memcpy(&bits, &scale, 4);
+  Q8Requant p = q8_make_requant(bits, zp, qmin, qmax);
+  q8_requant_enable_u(p, nmax);
+  if (!p.u_ok || q8_requant_mode(p) < 5) return 0;
+  for (size_t i = 0; i < n; i++) out[i] = (unsigned char) q8_requant(in[i], p);
+  return 1;
 }
 """
 
@@ -37,9 +47,16 @@ def hostcheck(tmp_path_factory):
     lib = C.CDLL(str(so))
     lib.hc_requant.argtypes = [C.c_size_t, C.c_void_p, C.c_float, C.c_uint8, C.c_uint8, C.c_uint8, C.c_void_p, C.c_int]
 
-    def run(x, scale, zp, qmin, qmax, slow=0):
+    lib.hc_requant_u.argtypes = [C.c_size_t, C.c_void_p, C.c_float, C.c_uint8, C.c_uint8, C.c_uint8, C.c_void_p,
+                                 C.c_longlong]
+    lib.hc_requant_u.restype = C.c_int
+
+    def run(x, scale, zp, qmin, qmax, slow=0, nmax=None):
         x = np.ascontiguousarray(x, dtype=np.int32)
         out = np.empty(x.shape, dtype=np.uint8)
+        if nmax is not None:
+            ok = lib.hc_requant_u(x.size, x.ctypes.data, float(np.float32(scale)), zp, qmin, qmax, out.ctypes.data, nmax)
+            return out if ok else None
         lib.hc_requant(x.size, x.ctypes.data, float(np.float32(scale)), zp, qmin, qmax, out.ctypes.data, slow)
         return out
     return run
@@ -63,6 +80,26 @@ def test_fused_requant_equals_specification(hostcheck, oracle_c):
             want = oracle_c.requantize_q31(x, scale, zp, qmin, qmax)
             assert np.array_equal(hostcheck(x, scale, zp, qmin, qmax), want), (scale, zp, qmin, qmax)
             assert np.array_equal(hostcheck(x, scale, zp, qmin, qmax, slow=1), want), (scale, zp, qmin, qmax)
+
+
+def test_u_form_requant_equals_specification(hostcheck, oracle_c):
+    """The 4-instruction "U" form (requant_math.h) under its accumulator bound |n| <= nmax, for bounds from a small
+    1x1 layer up to the full int32 range; it must either declare itself ineligible or be exact."""
+    rng = np.random.default_rng(12)
+    eligible = 0
+    for scale in _scales():
+        inv = 1.0 / float(scale)
+        for nmax in (2**31 - 1, 2**30, 2**27, 16 * 65025 + 2**20, 9 * 65025):
+            ties = np.array([int(round((k + 0.5) * inv)) + d for k in range(-130, 130) for d in (-1, 0, 1)], dtype=np.float64)
+            x = np.concatenate([[0, 1, -1, nmax, -nmax, nmax - 1, 1 - nmax], rng.integers(-nmax, nmax + 1, 3000),
+                                rng.integers(-300, 300, 1000) * inv, ties]).clip(-nmax, nmax).astype(np.int32)
+            for zp, qmin, qmax in ((0, 0, 255), (127, 1, 254), (255, 0, 255), (128, 128, 255), (100, 0, 128)):
+                got = hostcheck(x, scale, zp, qmin, qmax, nmax=nmax)
+                if got is None:
+                    continue
+                eligible += 1
+                assert np.array_equal(got, oracle_c.requantize_q31(x, scale, zp, qmin, qmax)), (scale, nmax, zp, qmin, qmax)
+    assert eligible > 1000
 
 
 @pytest.mark.parametrize("s", range(1, 32))
