@@ -330,6 +330,10 @@ struct EpiCtx {
   int row;             // row inside a sub-tile == TMEM lane
   int n_valid;         // valid output channels of this n-tile
   bool bulk;           // this item's output goes through the staging buffer and one bulk (1-D TMA) store
+  // hand-over barriers, touched as late / as early as the data dependences allow (both waits used to sit at the top
+  // of the item and showed up as the two largest stall sites of the kernel):
+  uint32_t out_free_bar, out_free_parity;  // waited on right before the warp's FIRST staging write of the item
+  uint32_t tmem_empty_bar;                 // arrived on right after the warp's LAST TMEM read of the item
 };
 
 // NB output bytes (NB/4 packed words, NB = 16 or 32) of row m, columns [c0, c0+NB) of the n-tile.
@@ -383,7 +387,8 @@ __device__ __forceinline__ void emit(const IgemmParams& p, const Item& it, const
 // FOLDED: the accumulator already contains bias and zero-point correction (extra UMMAs); otherwise
 // ("ones" mode) the folded bias comes from smem and -kzp*rowsum from accumulator column n_tile.
 template <int RQ, int W, bool FOLDED>
-__device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0) {
+__device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, bool first,
+                                              bool last) {
   int32_t v[W];
   const uint32_t taddr = e.tlane + j * p.n_mma + c0;
   if constexpr (W == 32) {
@@ -396,6 +401,10 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
     if (p.has_corr) tmem_ld1(e.tlane + j * p.n_mma + p.n_tile, rowsum);
   }
   tmem_ld_wait();
+  if (last) {  // the accumulator stage is drained as far as this warp is concerned: let the UMMA warp refill it now
+    tc_fence_before_sync();
+    mbar_arrive(e.tmem_empty_bar);
+  }
   if (p.dbg_acc != nullptr) {  // bring-up aid; v[] is only indexed with constants, so it stays in registers
     int32_t* d = p.dbg_acc + (((size_t) e.item * p.mt + j) * kTileM + e.row) * p.n_mma;
 #pragma unroll
@@ -435,6 +444,7 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
       w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 1], p.rq, p.shift_mul),
                            requant_dev<RQ>(v[4 * t + 2], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 3], p.rq, p.shift_mul));
   }
+  if (first && p.out_mode == 1) mbar_wait(e.out_free_bar, e.out_free_parity);  // the previous bulk store has left staging
   emit<W>(p, it, e, j, c0, w);
 }
 
@@ -447,11 +457,16 @@ __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& 
   const int per_sub = full + ((p.n_tile % W) ? 1 : 0);
   const int units = it.mt_eff * per_sub;
   int j = half / per_sub, c = half - j * per_sub;
+  if (half >= units) {  // nothing to read for this warp (tail item): release the stage right away
+    tc_fence_before_sync();
+    mbar_arrive(e.tmem_empty_bar);
+  }
   for (int u = half; u < units; u += 2) {
+    const bool first = u == half, last = u + 2 >= units;
     if (c < full) {
-      epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W);
+      epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W, first, last);
     } else {
-      epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
+      epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W, first, last);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
     }
     c += 2;
     while (c >= per_sub) {
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if constexpr (VEC == kVecTma) {
           if (p.b_resident && ltid != 0) continue;  // one thread drives the TMA; the others only matter when B streams
         }
-        mbar_wait(smem_u32(&ctl.empty[stage]), phase ^ 1);
+        mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
         const uint32_t a_stage = a_smem + stage * p.stage_bytes;
         if constexpr (VEC == kVecTma) {
           if (ltid == 0) {
@@ -662,7 +677,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         as_phase ^= 1;
       }
       const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
-      if (p.out_mode == 1) mbar_wait(smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1);  // staging buffer is free again
       mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
       tc_fence_after_sync();
       EpiCtx e;
@@ -674,6 +688,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       e.row = q * 32 + lane;
       e.n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
       e.bulk = bulk;
+      e.out_free_bar = smem_u32(&ctl.out_free[pair]);
+      e.out_free_parity = (k & 1) ^ 1;
+      e.tmem_empty_bar = smem_u32(&ctl.tmem_empty[as]);
       switch (p.rq_mode) {
         case 0: epilogue_dispatch<0>(p, it, e, half); break;
         case 1: epilogue_dispatch<1>(p, it, e, half); break;
@@ -683,9 +700,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         case 6: epilogue_dispatch<6>(p, it, e, half); break;
         default: epilogue_dispatch<3>(p, it, e, half); break;
       }
-      // done reading the accumulator stage: the UMMA warp may reuse it once the pair's 8 warps have arrived
-      tc_fence_before_sync();
-      mbar_arrive(smem_u32(&ctl.tmem_empty[as]));
       if (p.out_mode == 1) {
         fence_proxy_async_smem();  // staging writes (generic proxy) -> bulk copy (async proxy)
         mbar_arrive(smem_u32(&ctl.out_full[pair]));
@@ -699,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t k = 0;
       for (long long item = first + pair * step; item < p.total_items; item += 2 * step, k++) {
         const Item it = decode_item(p, item);
-        mbar_wait(smem_u32(&ctl.out_full[pair]), k & 1);
+        mbar_wait_relaxed(smem_u32(&ctl.out_full[pair]), k & 1, 20);
         if (it.m0 + (long long) it.mt_eff * kTileM <= p.M) {
           bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, (uint32_t) (it.mt_eff * kTileM * p.goc));
           bulk_commit();

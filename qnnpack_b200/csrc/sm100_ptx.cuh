@@ -42,6 +42,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For waiters that run far ahead of their producer (ring-slot recycling): back off between polls so that the spin
+// does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 
 // ----------------------------------------------------------------------------------------------
 // cp.async (LDGSTS) + completion onto an mbarrier
