@@ -154,9 +154,13 @@ class ClockSampler:
 
 
 def b200_main(args, rank, local_rank, world):
+    import faulthandler
+
     import numpy as np
     import torch
     import torch.distributed as dist
+
+    faulthandler.dump_traceback_later(240, exit=False)  # a hung collective or kernel leaves a stack trace on stderr
 
     os.environ["QNNP_CUDA_DEVICE"] = str(local_rank)
     torch.cuda.set_device(local_rank)
@@ -176,15 +180,15 @@ def b200_main(args, rank, local_rank, world):
     lib.set_stream(stream.cuda_stream)
 
     B = args.batch
-    stack = M.Stack(lib, seed=0, zero_weights=(rank != 0))
-    # one-time replication of the packed weights: rank 0 -> all, over NCCL (NVLink/NVSwitch)
+    # one-time replication of the model parameters: rank 0 -> all, one NCCL broadcast (NVLink/NVSwitch); every rank
+    # then plans and packs its own operators from identical numbers
+    params = M.make_params(seed=0, zero=(rank != 0))
     bcast_bytes = 0
     if world > 1:
         from qnnpack_b200 import shard as S
-        blobs = [torch.as_tensor(S.DeviceBytes(ptr, n), device=dev)
-                 for op in stack.ops for ptr, n in (lib.packed_weights(op), lib.packed_bias(op))]
-        bcast_bytes = S.replicate_from_rank0(blobs)
+        bcast_bytes = S.replicate_params_from_rank0([a for kb in params for a in kb], device=dev)
         torch.cuda.synchronize()
+    stack = M.Stack(lib, seed=0, params=params)
 
     cap = stack.max_activation_bytes(B)
     x_in = torch.randint(0, 256, (B * 224 * 224 * 3,), dtype=torch.uint8, device=dev)
@@ -338,6 +342,7 @@ def b200_main(args, rank, local_rank, world):
         "stack_frac_of_hbm_roofline": (stack.total_bytes(B) / 1e6 / peak_gbs) / ms_per_step,
     }
     print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
 

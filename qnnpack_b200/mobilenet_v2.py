@@ -120,18 +120,28 @@ def layer_params(layer: Layer, seed: int):
                               dilation=(1, 1), groups=layer.groups, gic=layer.gic, goc=layer.goc, **q)
 
 
+def make_params(seed: int = 0, zero: bool = False, only=None):
+    """[(kernel uint8, bias int32)] for every layer.  zero=True gives correctly shaped zero arrays — what a
+    rank other than 0 holds before qnnpack_b200.shard.replicate_params_from_rank0() fills them."""
+    out = []
+    for i, l in enumerate(layers() if only is None else only):
+        kernel, bias, _ = layer_params(l, seed * 1000 + i)
+        out.append((np.zeros_like(kernel), np.zeros_like(bias)) if zero else (kernel, bias))
+    return out
+
+
 class Stack:
     """The 53 operators created once through the C ABI; activations ping-pong between two buffers
     that the caller provides (device addresses for the product, NumPy arrays for the reference)."""
 
-    def __init__(self, lib, seed: int = 0, zero_weights: bool = False, only=None):
+    def __init__(self, lib, seed: int = 0, params=None, only=None):
         self.lib = lib
         self.layers = layers() if only is None else only
         self.ops = []
         for i, l in enumerate(self.layers):
             kernel, bias, kw = layer_params(l, seed * 1000 + i)
-            if zero_weights:  # ranks > 0: real weights arrive by broadcast of the packed blobs
-                kernel, bias = np.zeros_like(kernel), np.zeros_like(bias)
+            if params is not None:  # e.g. received from rank 0
+                kernel, bias = params[i]
             if l.kind == "fc":
                 st, op = lib.create_fully_connected(kernel, bias, **kw)
             else:

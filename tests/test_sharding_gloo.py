@@ -45,6 +45,11 @@ def _worker(rank, world, port, q):
         moved = S.replicate_from_rank0([kt, bt])
         assert moved == k.nbytes + b.nbytes
         assert np.array_equal(kt.numpy(), k) and np.array_equal(bt.numpy(), b)
+        # the form bench.py uses: a whole model's raw parameters in ONE broadcast, NumPy arrays updated in place
+        k2 = k.copy() if rank == 0 else np.zeros_like(k)
+        b2 = b.copy() if rank == 0 else np.zeros_like(b)
+        assert S.replicate_params_from_rank0([k2, b2]) == k.nbytes + b.nbytes
+        assert np.array_equal(k2, k) and np.array_equal(b2, b) and b2.dtype == np.int32
         lo, hi = S.shard_range(case["n"], world, rank)
         mine = co.convolution(np.ascontiguousarray(x[lo:hi]), kt.numpy(), bt.numpy(), **kw)
         full = co.convolution(x, k, b, **kw)
