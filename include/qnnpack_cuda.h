@@ -56,6 +56,16 @@ void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer);
 int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int folded, int bias_steps, int out[24]);
 int qnnp_cuda_debug_operator_is_folded(qnnp_operator_t op);
 
+/* Tiling of the depthwise tensor-core kernel (q8_dwconv_umma_sm100.cu) for a geometry; needs no GPU.  wmode: 0 = every
+ * w - kzp fits s8, 1 = kzp == 0 (u8 weights), 2 = w - kzp split into two s8 operands.
+ * out = {G, mt, xt, yt, nt, nb, Q, whole, planes, box_rows, box_px, plane_tx, plane_bytes, a_bytes, b_bytes, cg_bytes,
+ *        stage_bytes, num_stages, smem_total, x_org[2], a_off[5], a_lbo[5], sbo, nb_cols, b_signed, acc_stride, cblocks, cgs,
+ *        total_items, 0, 0}.  Returns 1, or 0 when the shape is not eligible (the CUDA-core depthwise kernels run instead). */
+int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, int in_w, int out_h, int out_w, int stride, int pad_top,
+                                int pad_left, int wmode, int out[40]);
+/* Launches of the depthwise tensor-core kernel since qnnp_initialize() (tests use it to prove the routing). */
+unsigned long long qnnp_cuda_debug_dw_umma_launch_count(void);
+
 /* Name of the kernel family an operator was routed to: "igemm-gemm", "igemm-conv", "dwconv3x3", "direct". */
 const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op);
 

@@ -57,6 +57,7 @@ class QnnpackLibrary:
         if self.is_cuda:
             L = self.lib
             L.qnnp_cuda_launch_count.restype = C.c_ulonglong
+            L.qnnp_cuda_debug_dw_umma_launch_count.restype = C.c_ulonglong
             L.qnnp_cuda_set_stream.argtypes = [C.c_void_p]
             L.qnnp_cuda_get_stream.restype = C.c_void_p
             L.qnnp_cuda_run_operator_async.argtypes = [C.c_void_p]
@@ -121,6 +122,9 @@ class QnnpackLibrary:
 
     def launch_count(self) -> int:
         return int(self.lib.qnnp_cuda_launch_count()) if self.is_cuda else 0
+
+    def dw_umma_launch_count(self) -> int:
+        return int(self.lib.qnnp_cuda_debug_dw_umma_launch_count()) if self.is_cuda else 0
 
     def packed_weights(self, op):
         p, n = C.c_void_p(), C.c_size_t()

@@ -43,6 +43,36 @@ struct DwStreamParams {
   Q8Requant rq;
 };
 
+// tcgen05 depthwise kernel (q8_dwconv_umma_sm100.cu): 3x3 depthwise as block-diagonal UMMAs over TMA-staged tiles
+constexpr int kDwTcTaps = 5;        // UMMAs (K = 32 = two taps) per (sub-tile, channel group): 9 taps + 1 empty slot
+constexpr int kDwTcMaxStages = 8;
+constexpr int kDwTcMaxG = 2;        // channel groups (16 channels each) per work item
+
+struct DwTcParams {
+  uint8_t* out;
+  const uint8_t* wpack;     // [channel group][kDwTcTaps][2 K-chunks][nb_cols rows][16 B]  block-diagonal B operands
+  const int32_t* bias_cls;  // [64 border classes][channels]: bias - izp * sum over the VALID taps of (w - kzp)
+  long long out_stride;
+  long long total_items;
+  int batch, channels, cgs, cblocks;     // cgs = channels / 16; cblocks = ceil(cgs / G)
+  int in_h, in_w, out_h, out_w, stride, pad_top, pad_left;
+  // work item = nb images x 16 row groups x (8 * mt) output columns x G channel groups
+  int G, mt, xt, yt, nt;    // x tiles per row, y tiles per image, image blocks
+  int nb, Q;                // images per item; row groups per image inside an item (16 when nb == 1)
+  int whole;                // 1: the item covers whole images (box rows = stride * Q per image, origin row -pad_top)
+  // smem stage: per channel group [planes][nb][box_rows][box_px][16 B] then the group's B block
+  int planes, box_rows, box_px, plane_tx, plane_bytes, a_bytes, b_bytes, cg_bytes, stage_bytes, num_stages, smem_total;
+                            // plane_tx = bytes one TMA box delivers; plane_bytes = its 128-byte-rounded smem slot
+  int x_org[2];             // plane x origin relative to the item's first output column (in plane pixels)
+  int a_off[kDwTcTaps], a_lbo[kDwTcTaps];  // byte offset of the first tap of UMMA u inside a group's A block; second-tap offset
+  int sbo;                  // bytes between the rows of consecutive row groups (stride * box_px * 16)
+  int nb_cols;              // accumulator columns per unit: 16, or 32 when w - kzp is split into two s8 operands
+  int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
+  int acc_stride, acc_stages;
+  int rq_mode;
+  Q8Requant rq;
+};
+
 struct DirectParams {
   const uint8_t* in;
   uint8_t* out;
@@ -59,6 +89,7 @@ struct DirectParams {
 
 cudaError_t launch_q8_dwconv3x3(DwParams p, int cv, cudaStream_t stream);
 cudaError_t launch_q8_dwconv3x3_stream(DwStreamParams p, cudaStream_t stream);
+cudaError_t launch_q8_dwconv3x3_umma(const DwTcParams& p, const void* tensor_map, int grid, cudaStream_t stream);
 cudaError_t launch_q8_direct_conv(const DirectParams& p, cudaStream_t stream);
 cudaError_t launch_q8_requantize(const int32_t* in, uint8_t* out, long long n, const Q8Requant& rq, cudaStream_t stream);
 

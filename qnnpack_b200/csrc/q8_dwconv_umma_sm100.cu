@@ -1,0 +1,311 @@
+// q8dwconv 3x3 for sm_100a on the tensor cores: depthwise convolution as block-diagonal UMMAs over TMA-staged tiles.
+//
+// Replaces (reference, paths relative to its root):
+//   src/operator-run.c:845-905  dwconv case -> q8dwconv_ukernel_up8x9__sse2 (src/q8dwconv/up8x9-sse2.c:14-482)
+//   src/indirection.c:81-150    (no pointer table: a tap is an address offset inside the staged tile)
+// for 3x3, dilation 1, stride 1 or 2, channels % 16 == 0; other depthwise shapes keep the CUDA-core kernels
+// (q8_dwconv_stream_sm100.cu, q8_dwconv_sm100.cu).
+//
+// Why tensor cores for a depthwise layer: on the CUDA cores the layer costs ~23 instructions per output byte
+// (window transposes + dp4a + requantisation) and runs at ~1/4 of the HBM roofline.  A UMMA with a DIAGONAL
+// 16x16 weight block per tap wastes 15/16 of its MACs, but B200 has ~60x more int8 MACs per byte of HBM traffic
+// than this layer needs, so the waste is free; what remains per output is the requantisation epilogue only.
+//
+// Data flow of one work item (nb images x 16 row groups x 8*mt output columns x G groups of 16 channels):
+//   TMA     : for each channel group ONE tensor-map box {16 B channels, box_px pixels, box_rows rows, nb images}
+//             (two boxes, even / odd input columns, when stride == 2: the input is viewed as [N][H][W/2][2][C]).
+//             In smem a pixel is 16 contiguous bytes, so 8 consecutive pixels ARE a K-major no-swizzle core matrix
+//             and a row group (8 output columns of one output row) is one 8-row slice of the UMMA's M = 128.
+//             Out-of-image pixels are zero-filled by the TMA unit (see bias_cls below).
+//   UMMA    : M = 128 (16 row groups: descriptor SBO = stride * row pitch), K = 32 = TWO taps (descriptor LBO = byte
+//             distance between the two taps' pixels), N = 16 channels.  B is diag(w_tap[c] - kzp) per tap, packed on
+//             the host.  9 taps -> 5 UMMAs per (sub-tile, channel group).  When w - kzp needs 9 bits it is split
+//             into two s8 operands that sit side by side in N (N = 32, the epilogue adds the halves).
+//   epilogue: TMEM -> registers, + bias_cls, Q31 requantisation, 16-byte global store per pixel.
+//   bias_cls: the reference pads with the input zero point, TMA pads with 0.  Both agree once the bias carries
+//             -izp * (sum of w - kzp over the taps that are INSIDE the image): 64 border classes (3 row bits x 3
+//             column bits) x channels, built on the host; interior pixels all use class 63.
+//
+// Same integers as the reference:  acc[c] = bias[c] + sum_valid_taps (a_tap[c] - izp) * (w_tap[c] - kzp).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "q8_dwconv_sm100.cuh"
+#include "requant_dev.cuh"
+#include "sm100_ptx.cuh"
+
+namespace q8 {
+namespace {
+
+constexpr int kEpiWarps = 16;
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kTmaWarp = kMmaWarp + 1;
+constexpr int kThreads = (kTmaWarp + 1) * 32;  // 576
+constexpr int kTmemCols = 512;
+
+struct __align__(8) Ctl {
+  uint64_t full[kDwTcMaxStages];
+  uint64_t empty[kDwTcMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+struct DwItem {
+  int cb;       // channel block (G groups of 16 channels)
+  int n0;       // first image
+  int oy0;      // first output row (0 in whole-image mode)
+  int ox0;      // first output column
+  int mt_eff;   // sub-tiles (8 columns) that contain at least one valid column
+  int g_eff;    // channel groups present in this block
+};
+
+// item = ((nblk * yt + ytile) * xt + xtile) * cblocks + cb: the channel blocks of one spatial tile are neighbours in
+// the schedule, so the CTAs that run them touch the same DRAM lines at about the same time.
+__device__ __forceinline__ DwItem decode_item(const DwTcParams& p, uint32_t item) {
+  DwItem it;
+  uint32_t r = item / (uint32_t) p.cblocks;
+  it.cb = (int) (item - r * (uint32_t) p.cblocks);
+  uint32_t q = r / (uint32_t) p.xt;
+  const uint32_t xtile = r - q * (uint32_t) p.xt;
+  r = q / (uint32_t) p.yt;
+  const uint32_t ytile = q - r * (uint32_t) p.yt;
+  it.n0 = (int) r * p.nb;
+  it.oy0 = (int) ytile * 16;
+  it.ox0 = (int) xtile * p.mt * 8;
+  const int left = (p.out_w - it.ox0 + 7) >> 3;
+  it.mt_eff = left < p.mt ? left : p.mt;
+  const int gl = p.cgs - it.cb * p.G;
+  it.g_eff = gl < p.G ? gl : p.G;
+  return it;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], "
+      "[%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+
+// One unit = 16 channels of one 8-column sub-tile for the warp's 32 TMEM lanes (4 row groups x 8 columns).
+template <int RQ, int NB>
+__device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t taddr, const int32_t* bias, uint8_t* dst, bool valid,
+                                              bool last, uint32_t tmem_empty_bar) {
+  int32_t v[16];
+  if constexpr (NB == 32) {
+    int32_t w[32];
+    tmem_ld32(taddr, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = w[i] + w[16 + i];  // (w - kzp) = A + B: the two operand halves
+  } else {
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+  }
+  if (last) {  // this warp has read everything it needs from the accumulator stage
+    tc_fence_before_sync();
+    mbar_arrive(tmem_empty_bar);
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int4 b = __ldg(reinterpret_cast<const int4*>(bias) + t);
+    int32_t y[4];
+    const int32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int32_t n = v[4 * t + i] + bb[i];  // for RQ 5/6 the table already carries the 2^31 offset of the "U" form
+      if constexpr (RQ == 5 || RQ == 6) {
+        int32_t r = q8_requant_u_unclamped((uint32_t) n, p.rq.u_m2, p.rq.u_k2, p.rq.u_sm);
+        if constexpr (RQ == 6) r = min(max(r, p.rq.qmin), p.rq.qmax);
+        y[i] = r;
+      } else {
+        y[i] = q8_requant(n, p.rq);
+      }
+    }
+    o[t] = pack_sat_u8x4(y[0], y[1], y[2], y[3]);
+  }
+  if (valid) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int S, int RQ, int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+    q8_dwconv3x3_umma_kernel(const __grid_constant__ DwTcParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ Ctl ctl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.num_stages; s++) {
+      mbar_init(smem_u32(&ctl.full[s]), 1);
+      mbar_init(smem_u32(&ctl.empty[s]), 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
+      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(smem_u32(&ctl.tmem_base));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl.tmem_base;
+  const uint32_t first = blockIdx.x, step = gridDim.x, total = (uint32_t) p.total_items;
+
+  if (warp == kTmaWarp) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t item = first; item < total; item += step) {
+        const DwItem it = decode_item(p, item);
+        mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
+        const uint32_t bar = smem_u32(&ctl.full[stage]);
+        const uint32_t dst0 = smem_base + (uint32_t) stage * p.stage_bytes;
+        mbar_arrive_expect_tx(bar, (uint32_t) it.g_eff * (uint32_t) (p.planes * p.plane_tx + p.b_bytes));
+        const int y0 = (p.whole ? 0 : it.oy0 * S) - p.pad_top;
+        for (int gi = 0; gi < it.g_eff; gi++) {
+          const int cg = it.cb * p.G + gi;
+          const uint32_t dst = dst0 + (uint32_t) gi * p.cg_bytes;
+          if constexpr (S == 1) {
+            tma_load_4d(dst, &tmap, cg * 16, it.ox0 + p.x_org[0], y0, it.n0, bar);
+          } else {
+            tma_load_5d(dst, &tmap, cg * 16, 0, it.ox0 + p.x_org[0], y0, it.n0, bar);
+            tma_load_5d(dst + p.plane_bytes, &tmap, cg * 16, 1, it.ox0 + p.x_org[1], y0, it.n0, bar);
+          }
+          bulk_g2s(dst + p.a_bytes, p.wpack + (size_t) cg * p.b_bytes, (uint32_t) p.b_bytes, bar);
+        }
+        if (++stage == p.num_stages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================== UMMA issue =====================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
+      uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
+#pragma unroll
+      for (int u = 0; u < kDwTcTaps; u++) {
+        adesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], (uint32_t) p.sbo);
+        bdesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 128);
+      }
+      int stage = 0, as = 0;
+      uint32_t phase = 0, as_phase = 0;
+      for (uint32_t item = first; item < total; item += step) {
+        const DwItem it = decode_item(p, item);
+        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
+        mbar_wait(smem_u32(&ctl.full[stage]), phase);
+        tc_fence_after_sync();
+        const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
+        const uint32_t d0 = tmem_base + (uint32_t) as * p.acc_stride;
+        // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: units are the
+        // inner loops, so consecutive instructions hit different accumulators
+#pragma unroll
+        for (int u = 0; u < kDwTcTaps; u++) {
+          for (int gi = 0; gi < it.g_eff; gi++) {
+            const uint32_t g16 = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
+            const uint64_t b = bdesc[u] + g16;
+            for (int j = 0; j < it.mt_eff; j++) {
+              umma_i8(d0 + (uint32_t) (gi * p.mt + j) * NB, adesc[u] + g16 + (uint32_t) j * 8, b, idesc, u > 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(smem_u32(&ctl.empty[stage]));    // smem stage may be refilled once these UMMAs have read it
+        umma_commit(smem_u32(&ctl.tmem_full[as]));   // accumulators complete
+        if (++stage == p.num_stages) stage = 0, phase ^= 1;
+        as ^= 1;
+        if (as == 0) as_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================================== epilogue (16 warps) =====================================
+    const int q = warp & 3, h = warp >> 2;
+    const int g = 4 * q + (lane >> 3), px = lane & 7;  // row group and column of this thread's TMEM lane
+    const int img = g / p.Q, oyl = g - img * p.Q;
+    int as = 0;
+    uint32_t as_phase = 0;
+    for (uint32_t item = first; item < total; item += step) {
+      const DwItem it = decode_item(p, item);
+      const int n = it.n0 + img, oy = it.oy0 + oyl;
+      const bool row_ok = img < p.nb && n < p.batch && oy < p.out_h;
+      const int iy0 = oy * S - p.pad_top;
+      const int rm = (iy0 >= 0 && iy0 < p.in_h ? 1 : 0) | (iy0 + 1 >= 0 && iy0 + 1 < p.in_h ? 2 : 0) |
+          (iy0 + 2 >= 0 && iy0 + 2 < p.in_h ? 4 : 0);
+      uint8_t* orow = p.out + ((size_t) ((long long) n * p.out_h + oy) * p.out_w) * p.out_stride;
+      const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
+      tc_fence_after_sync();
+      const uint32_t tbase = tmem_base + (uint32_t) as * p.acc_stride + ((uint32_t) (q * 32) << 16);
+      const int units = it.mt_eff * it.g_eff;
+      if (h >= units) {  // nothing to read (narrow tail item)
+        tc_fence_before_sync();
+        mbar_arrive(empty_bar);
+      }
+      for (int u = h; u < units; u += 4) {
+        const int j = it.g_eff == 2 ? (u >> 1) : u, gi = it.g_eff == 2 ? (u & 1) : 0;
+        const int ox = it.ox0 + 8 * j + px;
+        const int ix0 = ox * S - p.pad_left;
+        const int cm = (ix0 >= 0 && ix0 < p.in_w ? 1 : 0) | (ix0 + 1 >= 0 && ix0 + 1 < p.in_w ? 2 : 0) |
+            (ix0 + 2 >= 0 && ix0 + 2 < p.in_w ? 4 : 0);
+        const int cg = it.cb * p.G + gi;
+        const int32_t* bias = p.bias_cls + (size_t) (rm * 8 + cm) * p.channels + cg * 16;
+        uint8_t* dst = orow + (size_t) ox * p.out_stride + cg * 16;
+        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, bias, dst, row_ok && ox < p.out_w, u + 4 >= units,
+                              empty_bar);
+      }
+      as ^= 1;
+      if (as == 0) as_phase ^= 1;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int S, int RQ, int NB>
+cudaError_t launch_one(const DwTcParams& p, const CUtensorMap& tm, int grid, cudaStream_t stream) {
+  auto kern = q8_dwconv3x3_umma_kernel<S, RQ, NB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, p.smem_total, stream>>>(p, tm);
+  return cudaGetLastError();
+}
+
+template <int S, int NB>
+cudaError_t launch_rq(const DwTcParams& p, const CUtensorMap& tm, int grid, cudaStream_t stream) {
+  switch (p.rq_mode) {
+    case 5: return launch_one<S, 5, NB>(p, tm, grid, stream);
+    case 6: return launch_one<S, 6, NB>(p, tm, grid, stream);
+    default: return launch_one<S, 3, NB>(p, tm, grid, stream);  // generic q8_requant(): every other mode
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_q8_dwconv3x3_umma(const DwTcParams& p, const void* tensor_map, int grid, cudaStream_t stream) {
+  alignas(64) CUtensorMap tm;
+  memcpy(&tm, tensor_map, sizeof(tm));
+  if (p.stride == 1) {
+    return p.nb_cols == 32 ? launch_rq<1, 32>(p, tm, grid, stream) : launch_rq<1, 16>(p, tm, grid, stream);
+  }
+  return p.nb_cols == 32 ? launch_rq<2, 32>(p, tm, grid, stream) : launch_rq<2, 16>(p, tm, grid, stream);
+}
+
+}  // namespace q8

@@ -50,6 +50,7 @@ struct Library {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::atomic<unsigned long long> launches{0};
+  std::atomic<unsigned long long> dw_umma_launches{0};
   int32_t* dbg_acc = nullptr;
 };
 Library g_lib;
@@ -139,6 +140,125 @@ bool make_tmap_a(CUtensorMap* tm, const uint8_t* in, size_t M, size_t in_stride,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
+inline size_t ceil_div(size_t x, size_t q) { return (x + q - 1) / q; }
+constexpr int kCtlReserve = 2048;  // static SmemCtl + 1024-byte alignment slack
+
+// NHWC activations for the depthwise tensor-core kernel: stride 1 -> {C, W, H, N}; stride 2 -> {C, 2, W/2, H, N}
+// (even/odd input columns become a dimension of their own, so each parity plane is one dense box).
+bool make_tmap_dw(CUtensorMap* tm, const uint8_t* in, size_t N, size_t H, size_t W, size_t C, size_t in_stride, int s,
+                  int box_px, int box_rows, int nb) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint32_t estride[5] = {1, 1, 1, 1, 1};
+  if (s == 1) {
+    const cuuint64_t gdim[4] = {C, W, H, N};
+    const cuuint64_t gstride[3] = {in_stride, W * in_stride, H * W * in_stride};
+    const cuuint32_t box[4] = {16, (cuuint32_t) box_px, (cuuint32_t) box_rows, (cuuint32_t) nb};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  const cuuint64_t gdim[5] = {C, 2, W / 2, H, N};
+  const cuuint64_t gstride[4] = {in_stride, 2 * in_stride, W * in_stride, H * W * in_stride};
+  const cuuint32_t box[5] = {16, 1, (cuuint32_t) box_px, (cuuint32_t) box_rows, (cuuint32_t) nb};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int idiv_floor(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// Tiling of the depthwise tensor-core kernel (q8_dwconv_umma_sm100.cu).  Pure function of the geometry, so that the
+// CPU test can replay the smem addressing it prescribes.  Returns false when the shape is not eligible.
+bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad_top, int pad_left, int wmode, int smem_optin,
+                  q8::DwTcParams* p) {
+  if (C <= 0 || (C % 16) != 0 || (s != 1 && s != 2) || (s == 2 && (W % 2) != 0) || pad_top > 2 || pad_left > 2) return false;
+  if (batch <= 0 || OH <= 0 || OW <= 0) return false;
+  memset(p, 0, sizeof(*p));
+  p->batch = batch, p->channels = C, p->cgs = C / 16;
+  p->in_h = H, p->in_w = W, p->out_h = OH, p->out_w = OW, p->stride = s, p->pad_top = pad_top, p->pad_left = pad_left;
+  p->nb_cols = wmode == 2 ? 32 : 16;
+  p->b_signed = wmode == 1 ? 0 : 1;
+  p->G = p->cgs >= 2 ? 2 : 1;
+  p->cblocks = (p->cgs + p->G - 1) / p->G;
+  // rows: either 16-row tiles of one image, or whole (short) images stacked, each padded to Q row groups
+  const int rows_needed = s * (OH - 1) + 3;
+  const int Qw = (rows_needed + s - 1) / s;
+  p->whole = Qw <= 16 ? 1 : 0;
+  if (p->whole) {
+    p->Q = Qw;
+    p->nb = (16 + Qw - 1) / Qw;
+    p->box_rows = s * Qw;
+    p->yt = 1;
+  } else {
+    p->Q = 16;
+    p->nb = 1;
+    p->box_rows = 15 * s + 3;
+    p->yt = (OH + 15) / 16;
+  }
+  p->nt = (batch + p->nb - 1) / p->nb;
+  // columns: which plane and which plane-pixel offset each kernel column reads
+  int par[3], dx[3], dxmin[2] = {1 << 20, 1 << 20};
+  for (int kx = 0; kx < 3; kx++) {
+    if (s == 1) {
+      par[kx] = 0, dx[kx] = kx - pad_left;
+    } else {
+      par[kx] = ((kx - pad_left) % 2 + 2) % 2;
+      dx[kx] = idiv_floor(kx - pad_left - par[kx], 2);
+    }
+    if (dx[kx] < dxmin[par[kx]]) dxmin[par[kx]] = dx[kx];
+  }
+  p->planes = s;
+  for (int q = 0; q < 2; q++) p->x_org[q] = dxmin[q] == (1 << 20) ? 0 : dxmin[q];
+  int xoff[3], xoff_max = 0;
+  for (int kx = 0; kx < 3; kx++) {
+    xoff[kx] = dx[kx] - p->x_org[par[kx]];
+    if (xoff[kx] > xoff_max) xoff_max = xoff[kx];
+  }
+  // sub-tiles per item: bounded by the accumulator stage (256 TMEM columns) and by >= 3 smem stages
+  const int nsub = (OW + 7) / 8;
+  const int mt_cap_acc = 256 / p->nb_cols / p->G;
+  const int smem_max = smem_optin - kCtlReserve - 1024;
+  p->b_bytes = q8::kDwTcTaps * 2 * p->nb_cols * 16;
+  for (int cap = mt_cap_acc < 8 ? mt_cap_acc : 8; cap >= 1; cap--) {
+    const int xt = (nsub + cap - 1) / cap;
+    const int mt = (nsub + xt - 1) / xt;
+    const int box_px = 8 * mt + xoff_max;
+    if (box_px > 256 || p->box_rows > 256) continue;
+    const int plane_tx = p->nb * p->box_rows * box_px * 16;
+    const int plane_bytes = (int) round_up(plane_tx, 128);
+    const int a_bytes = p->planes * plane_bytes;
+    const int cg_bytes = (int) round_up(a_bytes + p->b_bytes, 128);
+    const int stage_bytes = p->G * cg_bytes;
+    int stages = smem_max / stage_bytes;
+    if (stages > q8::kDwTcMaxStages) stages = q8::kDwTcMaxStages;
+    if (stages < 3 && !(cap == 1 && stages >= 2)) continue;
+    p->mt = mt, p->xt = xt, p->box_px = box_px, p->plane_tx = plane_tx, p->plane_bytes = plane_bytes;
+    p->a_bytes = a_bytes, p->cg_bytes = cg_bytes, p->stage_bytes = stage_bytes, p->num_stages = stages;
+    break;
+  }
+  if (p->mt == 0) return false;
+  p->smem_total = p->num_stages * p->stage_bytes + 1024;
+  p->sbo = s * p->box_px * 16;
+  if ((p->sbo >> 4) > 0x3FFF) return false;
+  // UMMA u multiplies two taps (K = 2 x 16 channels): (u,0)+(u,2) for kernel rows u = 0..2, (0,1)+(1,1), (2,1)+nothing
+  const int t0[q8::kDwTcTaps][2] = {{0, 0}, {1, 0}, {2, 0}, {0, 1}, {2, 1}};
+  const int t1[q8::kDwTcTaps][2] = {{0, 2}, {1, 2}, {2, 2}, {1, 1}, {2, 1}};
+  for (int u = 0; u < q8::kDwTcTaps; u++) {
+    const int a0 = par[t0[u][1]] * p->plane_bytes + (t0[u][0] * p->box_px + xoff[t0[u][1]]) * 16;
+    const int a1 = par[t1[u][1]] * p->plane_bytes + (t1[u][0] * p->box_px + xoff[t1[u][1]]) * 16;
+    if (a1 < a0 || ((a1 - a0) >> 4) > 0x3FFF) return false;
+    p->a_off[u] = a0;
+    p->a_lbo[u] = a1 - a0;
+  }
+  p->acc_stride = p->mt * p->G * p->nb_cols;
+  p->acc_stages = 2;
+  p->total_items = (long long) p->nt * p->yt * p->xt * p->cblocks;
+  if (p->total_items >= (1ll << 31)) return false;
+  return true;
+}
+
 bool is_device_pointer(const void* ptr) {
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
@@ -148,8 +268,6 @@ bool is_device_pointer(const void* ptr) {
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
-inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
-inline size_t ceil_div(size_t x, size_t q) { return (x + q - 1) / q; }
 
 int pow2_align(uintptr_t v, int cap) {  // largest power of two <= cap dividing v (v == 0 -> cap)
   int a = cap;
@@ -193,6 +311,8 @@ struct qnnp_operator {
   uint32_t* d_dw_wa = nullptr;  // dw streaming kernel: packed taps, operands A and B
   uint32_t* d_dw_wb = nullptr;
   int dw_wmode = 0;
+  uint8_t* d_dwtc_w = nullptr;     // dw tensor-core kernel: block-diagonal B operands (null if channels % 16 != 0)
+  int32_t* d_dwtc_bias = nullptr;  // dw tensor-core kernel: [64 border classes][channels]
 
   // setup-time
   size_t batch = 0, in_h = 0, in_w = 0, out_h = 0, out_w = 0;
@@ -214,6 +334,8 @@ void free_operator(qnnp_operator* op) {
   cudaFree(op->d_bias);
   cudaFree(op->d_dw_wa);
   cudaFree(op->d_dw_wb);
+  cudaFree(op->d_dwtc_w);
+  cudaFree(op->d_dwtc_bias);
   cudaFree(op->d_in);
   cudaFree(op->d_out);
   delete op;
@@ -251,7 +373,6 @@ int32_t fold_bias(int32_t b, size_t k_total, uint8_t izp, uint8_t kzp, const uin
 // ------------------------------------------------------------------------------------------------
 // igemm planning + packing
 // ------------------------------------------------------------------------------------------------
-constexpr int kCtlReserve = 2048;  // static SmemCtl + 1024-byte alignment slack
 
 // Tiling + shared-memory plan of the tensor-core kernel; pure function of the operator shape (testable on a CPU box).
 struct IgemmPlan {
@@ -520,6 +641,44 @@ enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int3
   if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), fbias.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(op->d_dw_wa, wa.data(), wa.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(op->d_dw_wb, wb.data(), wb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  // tensor-core kernel operands (q8_dwconv_umma_sm100.cu)
+  if (e == cudaSuccess && (C % 16) == 0) {
+    const int nbc = op->dw_wmode == 2 ? 32 : 16;
+    const size_t ub = (size_t) 2 * nbc * 16;  // bytes of one UMMA's B operand: [2 K-chunks][nbc rows][16 B]
+    std::vector<uint8_t> wp((C / 16) * q8::kDwTcTaps * ub, 0);
+    const int t0[q8::kDwTcTaps] = {0, 3, 6, 1, 7}, t1[q8::kDwTcTaps] = {2, 5, 8, 4, -1};  // tap = ky*3 + kx
+    for (size_t cg = 0; cg < C / 16; cg++)
+      for (int u = 0; u < q8::kDwTcTaps; u++)
+        for (int ch = 0; ch < 2; ch++) {
+          const int tap = ch == 0 ? t0[u] : t1[u];
+          if (tap < 0) continue;
+          for (int n = 0; n < 16; n++) {
+            const int32_t d = w32[(size_t) tap * op->c_pad + cg * 16 + n];
+            int32_t da = op->dw_wmode == 1 ? (int32_t) kernel[(cg * 16 + n) * 9 + tap] : d, db = 0;
+            if (op->dw_wmode == 2) da = d >> 1, db = d - da;
+            uint8_t* blk = wp.data() + (cg * q8::kDwTcTaps + u) * ub + (size_t) ch * nbc * 16;
+            blk[(size_t) n * 16 + n] = (uint8_t) da;                               // B[n][k = n] of this K-chunk
+            if (nbc == 32) blk[(size_t) (16 + n) * 16 + n] = (uint8_t) db;         // second operand half: rows 16..31
+          }
+        }
+    // bias per border class: rows/columns of the 3x3 window that fall inside the image are bits of rm / cm
+    std::vector<int32_t> bc((size_t) 64 * C);
+    const bool uform = op->rq_mode == 5 || op->rq_mode == 6;
+    for (int rm = 0; rm < 8; rm++)
+      for (int cm = 0; cm < 8; cm++)
+        for (size_t c = 0; c < C; c++) {
+          int64_t sum = 0;
+          for (int ky = 0; ky < 3; ky++)
+            for (int kx = 0; kx < 3; kx++)
+              if (((rm >> ky) & 1) && ((cm >> kx) & 1)) sum += w32[(size_t) (ky * 3 + kx) * op->c_pad + c];
+          const int32_t v = (int32_t) ((int64_t) bias[c] - (int64_t) op->izp * sum);
+          bc[((size_t) rm * 8 + cm) * C + c] = uform ? (int32_t) ((uint32_t) v ^ 0x80000000u) : v;
+        }
+    e = cudaMalloc((void**) &op->d_dwtc_w, wp.size());
+    if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_dwtc_bias, bc.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_w, wp.data(), wp.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_bias, bc.data(), bc.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  }
   return map_cuda(e, "uploading depthwise weights");
 }
 
@@ -635,7 +794,23 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       cv = pow2_align((uintptr_t) op->groups, cv);
       const bool stream_ok = cv == 4 && op->dil_h == 1 && op->dil_w == 1 && op->stride_h == op->stride_w &&
           (op->stride_h == 1 || op->stride_h == 2) && getenv("QNNP_CUDA_DW_GENERIC") == nullptr;
-      if (stream_ok) {
+      // tensor-core path: channels % 16 == 0 and 16-byte aligned pixels (TMA boxes, 16-byte output stores)
+      q8::DwTcParams tp;
+      alignas(64) CUtensorMap dw_tmap;
+      const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && getenv("QNNP_CUDA_DW_NO_UMMA") == nullptr &&
+          ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
+          plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
+                       (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dw_wmode, g_lib.max_smem_optin, &tp) &&
+          make_tmap_dw(&dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
+                       tp.box_rows, tp.nb);
+      if (tc_ok) {
+        tp.out = out, tp.wpack = op->d_dwtc_w, tp.bias_cls = op->d_dwtc_bias;
+        tp.out_stride = (long long) op->out_stride;
+        tp.rq = op->rq, tp.rq_mode = op->rq_mode;
+        const long long grid = tp.total_items < g_lib.num_sms ? tp.total_items : g_lib.num_sms;
+        e = q8::launch_q8_dwconv3x3_umma(tp, &dw_tmap, (int) grid, stream);
+        if (e == cudaSuccess) g_lib.dw_umma_launches.fetch_add(1);
+      } else if (stream_ok) {
         q8::DwStreamParams sp{};
         sp.in = in, sp.out = out;
         sp.wa = op->d_dw_wa, sp.wb = op->d_dw_wb, sp.bias = op->d_bias;
@@ -954,6 +1129,7 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_bias(qnnp_operator_t op, 
   return qnnp_status_success;
 }
 QNNP_EXPORT unsigned long long qnnp_cuda_launch_count(void) { return g_lib.launches.load(); }
+QNNP_EXPORT unsigned long long qnnp_cuda_debug_dw_umma_launch_count(void) { return g_lib.dw_umma_launches.load(); }
 QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int folded, int bias_steps, int out[24]) {
   IgemmPlan pl;
   const int optin = g_lib.initialized ? g_lib.max_smem_optin : 232448;  // B200: 227 KB opt-in
@@ -963,6 +1139,19 @@ QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, 
                      pl.smem_a_off, pl.smem_stage_off, pl.smem_total, pl.bulk_capable, pl.folded, pl.bias_steps,
                      pl.blk_chunks, pl.good};
   for (int i = 0; i < 24; i++) out[i] = v[i];
+  return 1;
+}
+/* Depthwise tensor-core tiling for a geometry (CPU-callable): fills out[40], returns 0 when the shape is not eligible. */
+QNNP_EXPORT int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, int in_w, int out_h, int out_w, int stride,
+                                            int pad_top, int pad_left, int wmode, int out[40]) {
+  q8::DwTcParams p;
+  const int optin = g_lib.initialized ? g_lib.max_smem_optin : 232448;
+  if (!plan_dw_umma(channels, batch, in_h, in_w, out_h, out_w, stride, pad_top, pad_left, wmode, optin, &p)) return 0;
+  const int v[40] = {p.G, p.mt, p.xt, p.yt, p.nt, p.nb, p.Q, p.whole, p.planes, p.box_rows, p.box_px, p.plane_tx, p.plane_bytes,
+                     p.a_bytes, p.b_bytes, p.cg_bytes, p.stage_bytes, p.num_stages, p.smem_total, p.x_org[0], p.x_org[1],
+                     p.a_off[0], p.a_off[1], p.a_off[2], p.a_off[3], p.a_off[4], p.a_lbo[0], p.a_lbo[1], p.a_lbo[2], p.a_lbo[3],
+                     p.a_lbo[4], p.sbo, p.nb_cols, p.b_signed, p.acc_stride, p.cblocks, p.cgs, (int) p.total_items, 0, 0};
+  for (int i = 0; i < 40; i++) out[i] = v[i];
   return 1;
 }
 /* 1 if the operator runs in folded mode (bias + zero-point correction on the tensor core), 0 otherwise. */

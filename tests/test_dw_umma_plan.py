@@ -1,0 +1,158 @@
+"""CPU replay of the depthwise tensor-core kernel's addressing (qnnpack_b200/csrc/q8_dwconv_umma_sm100.cu).
+
+The host planner (qnnp_cuda_debug_plan_dwconv, callable without a GPU) prescribes the TMA boxes, the byte
+offsets of the two taps each UMMA reads (a_off / a_lbo), the row-group stride (sbo) and the work-item grid.
+This test plays the device's part in NumPy: it fills shared memory the way the TMA unit would (zero fill
+outside the image), gathers every UMMA operand row exactly where the descriptors point, applies the
+border-class bias, and compares the accumulators with a direct evaluation of the reference formula
+    acc[c] = bias[c] + sum over taps inside the image of (a_tap[c] - izp) * (w_tap[c] - kzp)
+(reference src/q8dwconv/up8x9-sse2.c:14-482 with the padding semantics of src/indirection.c:81-150).
+Hardware semantics (descriptor encoding, TMEM lanes) are covered by the GPU parity tests."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+NAMES = ("G mt xt yt nt nb Q whole planes box_rows box_px plane_tx plane_bytes a_bytes b_bytes cg_bytes stage_bytes "
+         "num_stages smem_total x_org0 x_org1 a_off0 a_off1 a_off2 a_off3 a_off4 a_lbo0 a_lbo1 a_lbo2 a_lbo3 a_lbo4 sbo "
+         "nb_cols b_signed acc_stride cblocks cgs total_items").split()
+T0 = (0, 3, 6, 1, 7)     # first tap (ky*3+kx) of UMMA u
+T1 = (2, 5, 8, 4, -1)    # second tap (-1: empty slot)
+SMEM_OPTIN = 232448
+
+
+@pytest.fixture(scope="module")
+def plan():
+    from qnnpack_b200 import build
+    lib = C.CDLL(build.build())
+    lib.qnnp_cuda_debug_plan_dwconv.argtypes = [C.c_int] * 10 + [C.POINTER(C.c_int)]
+
+    def f(c, n, h, w, s, pad=(1, 1), wmode=2):
+        oh = (h + 2 * pad[0] - 3) // s + 1
+        ow = (w + 2 * pad[1] - 3) // s + 1
+        out = (C.c_int * 40)()
+        ok = lib.qnnp_cuda_debug_plan_dwconv(c, n, h, w, oh, ow, s, pad[0], pad[1], wmode, out)
+        return (dict(zip(NAMES, out)), oh, ow) if ok else (None, oh, ow)
+    return f
+
+
+def replay(d, x, wk, bias, izp, kzp, s, pad, oh, ow):
+    """-> accumulators [N][OH][OW][C] computed by following the plan."""
+    n, h, w, c = x.shape
+    dk = wk.astype(np.int64) - kzp                      # [C][9]
+    acc = np.full((n, oh, ow, c), np.iinfo(np.int64).min, dtype=np.int64)
+    written = np.zeros((n, oh, ow, c), dtype=np.int32)
+    for item in range(d["total_items"]):
+        r, cb = divmod(item, d["cblocks"])
+        q, xtile = divmod(r, d["xt"])
+        nblk, ytile = divmod(q, d["yt"])
+        n0, oy0, ox0 = nblk * d["nb"], ytile * 16, xtile * d["mt"] * 8
+        mt_eff = min(d["mt"], (ow - ox0 + 7) // 8)
+        g_eff = min(d["G"], d["cgs"] - cb * d["G"])
+        y0 = (0 if d["whole"] else oy0 * s) - pad[0]
+        for gi in range(g_eff):
+            cg = cb * d["G"] + gi
+            # ---- TMA: one box per plane, zero fill outside the tensor
+            smem = np.zeros(d["a_bytes"] + 64 * 1024, dtype=np.uint8)   # slack: a wrong plan would read stale zeros
+            for par in range(d["planes"]):
+                xo = ox0 + (d["x_org0"], d["x_org1"])[par]
+                box = np.zeros((d["nb"], d["box_rows"], d["box_px"], 16), dtype=np.uint8)
+                for i in range(d["nb"]):
+                    for ry in range(d["box_rows"]):
+                        for rx in range(d["box_px"]):
+                            iy = y0 + ry
+                            ix = (xo + rx) if s == 1 else 2 * (xo + rx) + par
+                            inb = (xo + rx) >= 0 and ((xo + rx) < w if s == 1 else (xo + rx) < w // 2)
+                            if n0 + i < n and 0 <= iy < h and inb and 0 <= ix < w:
+                                box[i, ry, rx] = x[n0 + i, iy, ix, cg * 16:cg * 16 + 16]
+                smem[par * d["plane_bytes"]:par * d["plane_bytes"] + d["plane_tx"]] = box.reshape(-1)
+            # ---- UMMAs + epilogue for each sub-tile
+            for j in range(mt_eff):
+                a = np.zeros((128, 16), dtype=np.int64)
+                for u in range(5):
+                    for ch, tap in ((0, T0[u]), (1, T1[u])):
+                        if tap < 0:
+                            continue
+                        base = d["a_off%d" % u] + ch * d["a_lbo%d" % u] + j * 128
+                        for m in range(128):
+                            off = base + (m // 8) * d["sbo"] + (m % 8) * 16
+                            a[m] += smem[off:off + 16].astype(np.int64) * dk[cg * 16:cg * 16 + 16, tap]
+                for m in range(128):
+                    g, px = divmod(m, 8)
+                    img, oyl = divmod(g, d["Q"])
+                    nn, oy, ox = n0 + img, oy0 + oyl, ox0 + 8 * j + px
+                    if not (img < d["nb"] and nn < n and oy < oh and ox < ow):
+                        continue
+                    iy0, ix0 = oy * s - pad[0], ox * s - pad[1]
+                    ssum = np.zeros(16, dtype=np.int64)
+                    for ky in range(3):
+                        for kx in range(3):
+                            if 0 <= iy0 + ky < h and 0 <= ix0 + kx < w:
+                                ssum += dk[cg * 16:cg * 16 + 16, ky * 3 + kx]
+                    acc[nn, oy, ox, cg * 16:cg * 16 + 16] = a[m] + bias[cg * 16:cg * 16 + 16] - izp * ssum
+                    written[nn, oy, ox, cg * 16:cg * 16 + 16] += 1
+    assert (written == 1).all(), "every output must be produced exactly once"
+    return acc
+
+
+def direct(x, wk, bias, izp, kzp, s, pad, oh, ow):
+    n, h, w, c = x.shape
+    out = np.zeros((n, oh, ow, c), dtype=np.int64) + bias.astype(np.int64)
+    xi = x.astype(np.int64) - izp
+    dk = wk.astype(np.int64) - kzp
+    for oy in range(oh):
+        for ox in range(ow):
+            for ky in range(3):
+                for kx in range(3):
+                    iy, ix = oy * s - pad[0] + ky, ox * s - pad[1] + kx
+                    if 0 <= iy < h and 0 <= ix < w:
+                        out[:, oy, ox, :] += xi[:, iy, ix, :] * dk[:, ky * 3 + kx]
+    return out
+
+
+CASES = [
+    # (C, N, H, W, stride, pad)          geometry classes of MobileNetV2 at reduced sizes + odd ones
+    (16, 1, 20, 23, 1, (1, 1)),          # row tiles with a ragged last tile, ragged columns, one channel group
+    (48, 2, 7, 7, 1, (1, 1)),            # whole-image mode, two images stacked per item, odd group count
+    (32, 3, 14, 14, 1, (1, 1)),          # whole-image mode, Q = 16, batch not a multiple of nb
+    (32, 1, 40, 36, 2, (1, 1)),          # stride 2: parity planes, row tiles
+    (16, 3, 14, 14, 2, (1, 1)),          # stride 2, whole-image mode (Q = 8, nb = 2)
+    (32, 2, 9, 12, 1, (0, 0)),           # no padding
+    (16, 1, 18, 16, 2, (0, 0)),          # stride 2 without padding: planes swap roles
+    (16, 2, 5, 70, 1, (1, 1)),           # wide rows: several x tiles
+]
+
+
+@pytest.mark.parametrize("c,n,h,w,s,pad", CASES)
+def test_plan_addressing_reproduces_the_convolution(plan, c, n, h, w, s, pad):
+    d, oh, ow = plan(c, n, h, w, s, pad)
+    assert d is not None
+    assert d["smem_total"] <= SMEM_OPTIN - 1024 and d["num_stages"] >= 2
+    assert d["acc_stride"] <= 256 and d["mt"] * d["G"] * d["nb_cols"] == d["acc_stride"]
+    assert d["nb"] * d["Q"] >= 16 if d["whole"] else d["Q"] == 16
+    for u in range(5):  # descriptor fields are 14 bits of 16-byte units
+        assert d["a_off%d" % u] % 16 == 0 and d["a_lbo%d" % u] % 16 == 0 and 0 <= d["a_lbo%d" % u] < (1 << 18)
+    assert d["sbo"] % 16 == 0 and d["sbo"] < (1 << 18)
+    rng = np.random.default_rng(c * 1000 + h * 10 + s)
+    x = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+    wk = rng.integers(0, 256, (c, 9), dtype=np.uint8)
+    bias = rng.integers(-10000, 10000, c).astype(np.int64)
+    izp, kzp = 131, 77
+    got = replay(d, x, wk, bias, izp, kzp, s, pad, oh, ow)
+    want = direct(x, wk, bias, izp, kzp, s, pad, oh, ow)
+    assert np.array_equal(got, want)
+
+
+def test_mobilenet_depthwise_layers_are_eligible_and_fit(plan):
+    from qnnpack_b200 import mobilenet_v2 as M
+    for l in M.layers():
+        if l.kind != "dw":
+            continue
+        d, oh, ow = plan(l.cin, 4096, l.h, l.h, l.stride)
+        assert d is not None, l
+        assert d["num_stages"] >= 3 and d["smem_total"] <= SMEM_OPTIN - 1024, (l, d)
+
+
+def test_ineligible_shapes_fall_back(plan):
+    assert plan(24, 1, 8, 8, 1)[0] is None      # channels not a multiple of 16
+    assert plan(16, 1, 9, 9, 2)[0] is None      # stride 2 needs an even width

@@ -44,6 +44,37 @@ def test_q8dwconv(gpu_lib, golden, case):
     U.assert_same_bytes(U.run_conv(gpu_lib, case, x, k, b, kw), golden[f"conv/{case['name']}/y"], case["name"])
 
 
+# depthwise shapes that take the tcgen05 path (channels % 16 == 0, dense pixels): geometry classes of its planner —
+# 16-row tiles vs whole images stacked, one vs two parity planes, ragged tiles, every weight-operand mode, clamps
+DW_TC = dict(ks=(3, 3), pad=(1, 1, 1, 1))
+DW_TC_CASES = [
+    CS.conv_case("tc_c16_rows", 1, 20, 23, 16, 1, 1, **DW_TC),
+    CS.conv_case("tc_c48_7x7_stack2", 3, 7, 7, 48, 1, 1, **DW_TC),
+    CS.conv_case("tc_c32_14x14", 3, 14, 14, 32, 1, 1, **DW_TC),
+    CS.conv_case("tc_c32_s2_rows", 1, 40, 36, 32, 1, 1, stride=(2, 2), **DW_TC),
+    CS.conv_case("tc_c16_s2_whole", 3, 14, 14, 16, 1, 1, stride=(2, 2), **DW_TC),
+    CS.conv_case("tc_c32_nopad", 2, 9, 12, 32, 1, 1, ks=(3, 3)),
+    CS.conv_case("tc_c16_s2_nopad", 1, 18, 16, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
+    CS.conv_case("tc_c16_wide", 2, 5, 70, 16, 1, 1, **DW_TC),
+    CS.conv_case("tc_c64_kzp128_s8", 2, 17, 17, 64, 1, 1, kzp=128, **DW_TC),      # w - kzp fits s8: one operand
+    CS.conv_case("tc_c64_kzp0_u8", 2, 17, 17, 64, 1, 1, kzp=0, izp=3, **DW_TC),    # u8 weights
+    CS.conv_case("tc_c32_kzp255", 1, 12, 12, 32, 1, 1, kzp=255, izp=255, **DW_TC),
+    CS.conv_case("tc_c32_clamp", 1, 12, 12, 32, 1, 1, qmin=40, qmax=200, **DW_TC),
+    CS.conv_case("tc_c160_112", 1, 112, 112, 160, 1, 1, **DW_TC),
+    CS.conv_case("tc_c32_out_stride", 1, 10, 10, 32, 1, 1, out_extra=16, **DW_TC),
+    CS.conv_case("tc_c32_in_stride", 1, 10, 10, 32, 1, 1, in_extra=16, **DW_TC),
+]
+
+
+@pytest.mark.parametrize("case", DW_TC_CASES, ids=lambda c: c["name"])
+def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case):
+    x, k, b, kw = U.conv_setup(case)
+    before = gpu_lib.dw_umma_launch_count()
+    got = U.run_conv(gpu_lib, case, x, k, b, kw)
+    assert gpu_lib.dw_umma_launch_count() == before + 1, "expected the tcgen05 depthwise kernel"
+    U.assert_same_bytes(got, U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
+
+
 # ---- q8gemm through the fully-connected operator ------------------------------------------------------
 @pytest.mark.parametrize("case", CS.GEMM_UKERNEL_CASES, ids=lambda c: c["name"])
 def test_q8gemm(gpu_lib, golden, case):
