@@ -46,7 +46,7 @@ struct DwStreamParams {
 // tcgen05 depthwise kernel (q8_dwconv_umma_sm100.cu): 3x3 depthwise as block-diagonal UMMAs over TMA-staged tiles
 constexpr int kDwTcTaps = 5;        // UMMAs (K = 32 = two taps) per (sub-tile, channel group): 9 taps + 1 empty slot
 constexpr int kDwTcMaxStages = 8;
-constexpr int kDwTcMaxG = 2;        // channel groups (16 channels each) per work item
+constexpr int kDwTcMaxG = 8;        // channel groups (16 channels each) per work item
 
 struct DwTcParams {
   uint8_t* out;

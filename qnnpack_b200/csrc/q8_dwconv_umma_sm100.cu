@@ -40,9 +40,11 @@ namespace q8 {
 namespace {
 
 constexpr int kEpiWarps = 16;
-constexpr int kMmaWarp = kEpiWarps;
-constexpr int kTmaWarp = kMmaWarp + 1;
-constexpr int kThreads = (kTmaWarp + 1) * 32;  // 576
+constexpr int kMmaWarp = kEpiWarps;            // first of the UMMA-issuing warps (it also owns the TMEM allocation)
+constexpr int kMmaWarps = 4;                   // one lane each; they split the units of an item (see below)
+constexpr int kTmaWarp = kMmaWarp + kMmaWarps;
+constexpr int kThreads = (kTmaWarp + 1) * 32;  // 672
+constexpr int kMaxUnitsPerMmaWarp = 4;         // 16 units (mt * G <= 16) over 4 warps
 constexpr int kTmemCols = 512;
 
 struct __align__(8) Ctl {
@@ -82,6 +84,12 @@ __device__ __forceinline__ DwItem decode_item(const DwTcParams& p, uint32_t item
   return it;
 }
 
+// unit index -> (sub-tile j, channel group gi) with gi fastest; inv = ceil(2^16 / g_eff) (exact for un < 256)
+__device__ __forceinline__ void unit_split(int un, int g_eff, uint32_t inv, int& j, int& gi) {
+  j = (int) (((uint32_t) un * inv) >> 16);
+  gi = un - j * g_eff;
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
@@ -99,9 +107,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
 }
 
 // One unit = 16 channels of one 8-column sub-tile for the warp's 32 TMEM lanes (4 row groups x 8 columns).
+// The bias words are fetched BEFORE the TMEM load is waited for (the wait is a compiler barrier for memory operations).
 template <int RQ, int NB>
 __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t taddr, const int32_t* bias, uint8_t* dst, bool valid,
                                               bool last, uint32_t tmem_empty_bar) {
+  int4 b[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) b[t] = __ldg(reinterpret_cast<const int4*>(bias) + t);
   int32_t v[16];
   if constexpr (NB == 32) {
     int32_t w[32];
@@ -120,9 +132,8 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
   uint32_t o[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) {
-    const int4 b = __ldg(reinterpret_cast<const int4*>(bias) + t);
     int32_t y[4];
-    const int32_t bb[4] = {b.x, b.y, b.z, b.w};
+    const int32_t bb[4] = {b[t].x, b[t].y, b[t].z, b[t].w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int32_t n = v[4 * t + i] + bb[i];  // for RQ 5/6 the table already carries the 2^31 offset of the "U" form
@@ -150,10 +161,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (tid == 0) {
     for (int s = 0; s < p.num_stages; s++) {
       mbar_init(smem_u32(&ctl.full[s]), 1);
-      mbar_init(smem_u32(&ctl.empty[s]), 1);
+      mbar_init(smem_u32(&ctl.empty[s]), kMmaWarps);  // one tcgen05.commit per issuing warp
     }
     for (int s = 0; s < 2; s++) {
-      mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
+      mbar_init(smem_u32(&ctl.tmem_full[s]), kMmaWarps);
       mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiWarps * 32);
     }
     fence_mbar_init();
@@ -191,9 +202,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (++stage == p.num_stages) stage = 0, phase ^= 1;
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ===================================== UMMA issue =====================================
+  } else if (warp >= kMmaWarp && warp < kMmaWarp + kMmaWarps) {
+    // ===================================== UMMA issue (4 warps, one lane each) =====================================
+    // This layer needs one small UMMA (N = 16/32) per ~400 outputs, i.e. one every ~40 cycles per SM: more than a single
+    // thread can issue (descriptor arithmetic + the instruction itself cost it ~100 cycles each, measured).  So four
+    // warps — one per SM sub-partition — issue concurrently; warp w owns the units w, w+4, ... of every item.
     if (lane == 0) {
+      const int w = warp - kMmaWarp;
       const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
       uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
 #pragma unroll
@@ -205,25 +220,34 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0, as_phase = 0;
       for (uint32_t item = first; item < total; item += step) {
         const DwItem it = decode_item(p, item);
+        const int units = it.mt_eff * it.g_eff;
+        const uint32_t inv = (65536u + (uint32_t) it.g_eff - 1) / (uint32_t) it.g_eff;
+        // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
+        uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
+        const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
+#pragma unroll
+        for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
+          int j, gi;
+          unit_split(w + i * kMmaWarps, it.g_eff, inv, j, gi);
+          b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
+          a16[i] = b16[i] + (uint32_t) j * 8;
+          dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
+        }
         mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
         mbar_wait(smem_u32(&ctl.full[stage]), phase);
         tc_fence_after_sync();
-        const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
-        const uint32_t d0 = tmem_base + (uint32_t) as * p.acc_stride;
-        // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: units are the
-        // inner loops, so consecutive instructions hit different accumulators
+        // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
+        // outer loop, so consecutive instructions hit different accumulators
 #pragma unroll
         for (int u = 0; u < kDwTcTaps; u++) {
-          for (int gi = 0; gi < it.g_eff; gi++) {
-            const uint32_t g16 = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
-            const uint64_t b = bdesc[u] + g16;
-            for (int j = 0; j < it.mt_eff; j++) {
-              umma_i8(d0 + (uint32_t) (gi * p.mt + j) * NB, adesc[u] + g16 + (uint32_t) j * 8, b, idesc, u > 0 ? 1u : 0u);
-            }
+#pragma unroll
+          for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
+            if (w + i * kMmaWarps < units)
+              umma_i8(tmem_base + dcol[i], adesc[u] + a16[i], bdesc[u] + b16[i], idesc, u > 0 ? 1u : 0u);
           }
         }
         umma_commit(smem_u32(&ctl.empty[stage]));    // smem stage may be refilled once these UMMAs have read it
-        umma_commit(smem_u32(&ctl.tmem_full[as]));   // accumulators complete
+        umma_commit(smem_u32(&ctl.tmem_full[as]));   // this warp's share of the accumulators is complete
         if (++stage == p.num_stages) stage = 0, phase ^= 1;
         as ^= 1;
         if (as == 0) as_phase ^= 1;
@@ -245,24 +269,36 @@ __global__ void __launch_bounds__(kThreads, 1)
           (iy0 + 2 >= 0 && iy0 + 2 < p.in_h ? 4 : 0);
       uint8_t* orow = p.out + ((size_t) ((long long) n * p.out_h + oy) * p.out_w) * p.out_stride;
       const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
-      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
+      mbar_wait_relaxed(smem_u32(&ctl.tmem_full[as]), as_phase, 20);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + (uint32_t) as * p.acc_stride + ((uint32_t) (q * 32) << 16);
+      // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, gi fastest); pixel, border-class
+      // and address arithmetic are redone only when j changes
       const int units = it.mt_eff * it.g_eff;
+      const uint32_t inv = (65536u + (uint32_t) it.g_eff - 1) / (uint32_t) it.g_eff;
       if (h >= units) {  // nothing to read (narrow tail item)
         tc_fence_before_sync();
         mbar_arrive(empty_bar);
       }
-      for (int u = h; u < units; u += 4) {
-        const int j = it.g_eff == 2 ? (u >> 1) : u, gi = it.g_eff == 2 ? (u & 1) : 0;
-        const int ox = it.ox0 + 8 * j + px;
-        const int ix0 = ox * S - p.pad_left;
-        const int cm = (ix0 >= 0 && ix0 < p.in_w ? 1 : 0) | (ix0 + 1 >= 0 && ix0 + 1 < p.in_w ? 2 : 0) |
-            (ix0 + 2 >= 0 && ix0 + 2 < p.in_w ? 4 : 0);
-        const int cg = it.cb * p.G + gi;
-        const int32_t* bias = p.bias_cls + (size_t) (rm * 8 + cm) * p.channels + cg * 16;
-        uint8_t* dst = orow + (size_t) ox * p.out_stride + cg * 16;
-        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, bias, dst, row_ok && ox < p.out_w, u + 4 >= units,
+      int j_cur = -1;
+      const int32_t* bias = nullptr;
+      uint8_t* dst = nullptr;
+      bool valid = false;
+      for (int un = h; un < units; un += 4) {
+        int j, gi;
+        unit_split(un, it.g_eff, inv, j, gi);
+        if (j != j_cur) {
+          j_cur = j;
+          const int ox = it.ox0 + 8 * j + px;
+          const int ix0 = ox * S - p.pad_left;
+          const int cm = (ix0 >= 0 && ix0 < p.in_w ? 1 : 0) | (ix0 + 1 >= 0 && ix0 + 1 < p.in_w ? 2 : 0) |
+              (ix0 + 2 >= 0 && ix0 + 2 < p.in_w ? 4 : 0);
+          const int c0 = it.cb * p.G * 16;
+          bias = p.bias_cls + (size_t) (rm * 8 + cm) * p.channels + c0;
+          dst = orow + (size_t) ox * p.out_stride + c0;
+          valid = row_ok && ox < p.out_w;
+        }
+        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, bias + gi * 16, dst + gi * 16, valid, un + 4 >= units,
                               empty_bar);
       }
       as ^= 1;

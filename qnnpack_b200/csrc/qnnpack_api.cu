@@ -180,8 +180,6 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   p->in_h = H, p->in_w = W, p->out_h = OH, p->out_w = OW, p->stride = s, p->pad_top = pad_top, p->pad_left = pad_left;
   p->nb_cols = wmode == 2 ? 32 : 16;
   p->b_signed = wmode == 1 ? 0 : 1;
-  p->G = p->cgs >= 2 ? 2 : 1;
-  p->cblocks = (p->cgs + p->G - 1) / p->G;
   // rows: either 16-row tiles of one image, or whole (short) images stacked, each padded to Q row groups
   const int rows_needed = s * (OH - 1) + 3;
   const int Qw = (rows_needed + s - 1) / s;
@@ -216,12 +214,14 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
     xoff[kx] = dx[kx] - p->x_org[par[kx]];
     if (xoff[kx] > xoff_max) xoff_max = xoff[kx];
   }
-  // sub-tiles per item: bounded by the accumulator stage (256 TMEM columns) and by >= 3 smem stages
+  // sub-tiles (mt) and channel groups (G) per item: mt * G units share an accumulator stage (256 TMEM columns) and are
+  // what the 16 epilogue warps / 4 UMMA warps split among themselves, so narrow images take more channel groups.
+  // G >= 2 whenever possible: the two 16-byte halves of every 32-byte sector are then moved by the same item.
   const int nsub = (OW + 7) / 8;
-  const int mt_cap_acc = 256 / p->nb_cols / p->G;
+  const int umax = 256 / p->nb_cols;  // 8 (split operands) or 16 units
   const int smem_max = smem_optin - kCtlReserve - 1024;
   p->b_bytes = q8::kDwTcTaps * 2 * p->nb_cols * 16;
-  for (int cap = mt_cap_acc < 8 ? mt_cap_acc : 8; cap >= 1; cap--) {
+  for (int cap = umax / 2 < 8 ? umax / 2 : 8; cap >= 1 && p->mt == 0; cap--) {
     const int xt = (nsub + cap - 1) / cap;
     const int mt = (nsub + xt - 1) / xt;
     const int box_px = 8 * mt + xoff_max;
@@ -230,15 +230,21 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
     const int plane_bytes = (int) round_up(plane_tx, 128);
     const int a_bytes = p->planes * plane_bytes;
     const int cg_bytes = (int) round_up(a_bytes + p->b_bytes, 128);
-    const int stage_bytes = p->G * cg_bytes;
-    int stages = smem_max / stage_bytes;
-    if (stages > q8::kDwTcMaxStages) stages = q8::kDwTcMaxStages;
-    if (stages < 3 && !(cap == 1 && stages >= 2)) continue;
-    p->mt = mt, p->xt = xt, p->box_px = box_px, p->plane_tx = plane_tx, p->plane_bytes = plane_bytes;
-    p->a_bytes = a_bytes, p->cg_bytes = cg_bytes, p->stage_bytes = stage_bytes, p->num_stages = stages;
-    break;
+    int G = umax / mt;
+    if (G > q8::kDwTcMaxG) G = q8::kDwTcMaxG;
+    if (G > p->cgs) G = p->cgs;
+    for (; G >= 1; G = (G > 2 ? G - 1 : G - 1)) {
+      const int stage_bytes = G * cg_bytes;
+      int stages = smem_max / stage_bytes;
+      if (stages > q8::kDwTcMaxStages) stages = q8::kDwTcMaxStages;
+      if (stages < 3 && !(cap == 1 && G == 1 && stages >= 2)) continue;
+      p->G = G, p->mt = mt, p->xt = xt, p->box_px = box_px, p->plane_tx = plane_tx, p->plane_bytes = plane_bytes;
+      p->a_bytes = a_bytes, p->cg_bytes = cg_bytes, p->stage_bytes = stage_bytes, p->num_stages = stages;
+      break;
+    }
   }
   if (p->mt == 0) return false;
+  p->cblocks = (p->cgs + p->G - 1) / p->G;
   p->smem_total = p->num_stages * p->stage_bytes + 1024;
   p->sbo = s * p->box_px * 16;
   if ((p->sbo >> 4) > 0x3FFF) return false;
