@@ -69,6 +69,7 @@ struct DwTcParams {
   int nb_cols;              // accumulator columns per unit: 16, or 32 when w - kzp is split into two s8 operands
   int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
   int acc_stride, acc_stages;
+  int epi_poll_ns;          // back-off of the epilogue warps' accumulator poll (0 = spin)
   int rq_mode;
   Q8Requant rq;
 };

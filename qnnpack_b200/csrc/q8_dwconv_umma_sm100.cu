@@ -150,6 +150,61 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
   if (valid) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// UMMA-issuing role of warp kMmaWarp + W: lane 0 alone runs the loop.  (Keeping the whole warp in the loop and
+// predicating only the tcgen05 instructions is far worse: nvcc wraps every tcgen05.mma in an elect/broadcast loop that
+// then iterates once per ACTIVE lane — measured 3x slower.)
+template <int NB, int W>
+__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t smem_base, uint32_t tmem_base, int lane,
+                                         uint32_t first, uint32_t step, uint32_t total) {
+    if (lane == 0) {
+      constexpr int w = W;
+      const uint32_t tmem_u = tmem_base;
+      const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
+      uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
+#pragma unroll
+      for (int u = 0; u < kDwTcTaps; u++) {
+        adesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], (uint32_t) p.sbo);
+        bdesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 128);
+      }
+      int stage = 0, as = 0;
+      uint32_t phase = 0, as_phase = 0;
+      for (uint32_t item = first; item < total; item += step) {
+        const DwItem it = decode_item(p, item);
+        const int units = it.mt_eff * it.g_eff;
+        const uint32_t inv = (65536u + (uint32_t) it.g_eff - 1) / (uint32_t) it.g_eff;
+        // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
+        uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
+        const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
+#pragma unroll
+        for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
+          int j, gi;
+          unit_split(w + i * kMmaWarps, it.g_eff, inv, j, gi);
+          b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
+          a16[i] = b16[i] + (uint32_t) j * 8;
+          dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
+        }
+        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
+        mbar_wait(smem_u32(&ctl.full[stage]), phase);
+        tc_fence_after_sync();
+        // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
+        // outer loop, so consecutive instructions hit different accumulators
+#pragma unroll
+        for (int u = 0; u < kDwTcTaps; u++) {
+#pragma unroll
+          for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
+            if (w + i * kMmaWarps < units)
+              umma_i8(tmem_u + dcol[i], adesc[u] + a16[i], bdesc[u] + b16[i], idesc, u > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&ctl.empty[stage]));    // smem stage may be refilled once these UMMAs have read it
+        umma_commit(smem_u32(&ctl.tmem_full[as]));   // this warp's share of the accumulators is complete
+        if (++stage == p.num_stages) stage = 0, phase ^= 1;
+        as ^= 1;
+        if (as == 0) as_phase ^= 1;
+      }
+    }
+}
+
 template <int S, int RQ, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
     q8_dwconv3x3_umma_kernel(const __grid_constant__ DwTcParams p, const __grid_constant__ CUtensorMap tmap) {
@@ -204,54 +259,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp >= kMmaWarp && warp < kMmaWarp + kMmaWarps) {
     // ===================================== UMMA issue (4 warps, one lane each) =====================================
-    // This layer needs one small UMMA (N = 16/32) per ~400 outputs, i.e. one every ~40 cycles per SM: more than a single
-    // thread can issue (descriptor arithmetic + the instruction itself cost it ~100 cycles each, measured).  So four
-    // warps — one per SM sub-partition — issue concurrently; warp w owns the units w, w+4, ... of every item.
-    if (lane == 0) {
-      const int w = warp - kMmaWarp;
-      const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
-      uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
-#pragma unroll
-      for (int u = 0; u < kDwTcTaps; u++) {
-        adesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], (uint32_t) p.sbo);
-        bdesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 128);
-      }
-      int stage = 0, as = 0;
-      uint32_t phase = 0, as_phase = 0;
-      for (uint32_t item = first; item < total; item += step) {
-        const DwItem it = decode_item(p, item);
-        const int units = it.mt_eff * it.g_eff;
-        const uint32_t inv = (65536u + (uint32_t) it.g_eff - 1) / (uint32_t) it.g_eff;
-        // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
-        uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
-        const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
-#pragma unroll
-        for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
-          int j, gi;
-          unit_split(w + i * kMmaWarps, it.g_eff, inv, j, gi);
-          b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
-          a16[i] = b16[i] + (uint32_t) j * 8;
-          dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
-        }
-        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
-        mbar_wait(smem_u32(&ctl.full[stage]), phase);
-        tc_fence_after_sync();
-        // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
-        // outer loop, so consecutive instructions hit different accumulators
-#pragma unroll
-        for (int u = 0; u < kDwTcTaps; u++) {
-#pragma unroll
-          for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
-            if (w + i * kMmaWarps < units)
-              umma_i8(tmem_base + dcol[i], adesc[u] + a16[i], bdesc[u] + b16[i], idesc, u > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(smem_u32(&ctl.empty[stage]));    // smem stage may be refilled once these UMMAs have read it
-        umma_commit(smem_u32(&ctl.tmem_full[as]));   // this warp's share of the accumulators is complete
-        if (++stage == p.num_stages) stage = 0, phase ^= 1;
-        as ^= 1;
-        if (as == 0) as_phase ^= 1;
-      }
+    // This layer needs one small UMMA (N = 16/32) per ~400 outputs, i.e. one every ~40 cycles per SM.  nvcc wraps every
+    // tcgen05.mma in an elect/broadcast sequence (~27 instructions), and an issuing warp shares its sub-partition with
+    // four busy epilogue warps, so one thread manages only one UMMA per ~100 cycles (measured).  Four warps — one per
+    // sub-partition — issue concurrently; warp w owns the units w, w+4, ... of every item.  (Eight issuing warps were
+    // measured 3x SLOWER than four.)
+    switch (warp - kMmaWarp) {
+      case 0: mma_role<NB, 0>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
+      case 1: mma_role<NB, 1>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
+      case 2: mma_role<NB, 2>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
+      default: mma_role<NB, 3>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
     }
   } else {
     // ===================================== epilogue (16 warps) =====================================
@@ -269,7 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           (iy0 + 2 >= 0 && iy0 + 2 < p.in_h ? 4 : 0);
       uint8_t* orow = p.out + ((size_t) ((long long) n * p.out_h + oy) * p.out_w) * p.out_stride;
       const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
-      mbar_wait_relaxed(smem_u32(&ctl.tmem_full[as]), as_phase, 20);
+      if (p.epi_poll_ns > 0) {
+        mbar_wait_relaxed(smem_u32(&ctl.tmem_full[as]), as_phase, (uint32_t) p.epi_poll_ns);
+      } else {
+        mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
+      }
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + (uint32_t) as * p.acc_stride + ((uint32_t) (q * 32) << 16);
       // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, gi fastest); pixel, border-class

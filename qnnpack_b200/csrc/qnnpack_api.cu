@@ -803,7 +803,13 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       // tensor-core path: channels % 16 == 0 and 16-byte aligned pixels (TMA boxes, 16-byte output stores)
       q8::DwTcParams tp;
       alignas(64) CUtensorMap dw_tmap;
+      // (measured on MobileNetV2 at batch 4096: the tcgen05 kernel wins everywhere except stride-2 layers tiled by rows,
+      // where one channel group per item fits and the CUDA-core streaming kernel is ~8% faster; QNNP_CUDA_DW_UMMA=1
+      // forces the tensor-core path for every eligible shape, QNNP_CUDA_DW_NO_UMMA=1 disables it)
+      const bool force_tc = getenv("QNNP_CUDA_DW_UMMA") != nullptr;
+      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32;
       const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && getenv("QNNP_CUDA_DW_NO_UMMA") == nullptr &&
+          (force_tc || !s2_rows) &&
           ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
           plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
                        (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dw_wmode, g_lib.max_smem_optin, &tp) &&
@@ -813,6 +819,7 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         tp.out = out, tp.wpack = op->d_dwtc_w, tp.bias_cls = op->d_dwtc_bias;
         tp.out_stride = (long long) op->out_stride;
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
+        if (const char* ev = getenv("QNNP_CUDA_DW_POLL_NS")) tp.epi_poll_ns = atoi(ev);
         const long long grid = tp.total_items < g_lib.num_sms ? tp.total_items : g_lib.num_sms;
         e = q8::launch_q8_dwconv3x3_umma(tp, &dw_tmap, (int) grid, stream);
         if (e == cudaSuccess) g_lib.dw_umma_launches.fetch_add(1);

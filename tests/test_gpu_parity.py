@@ -67,7 +67,8 @@ DW_TC_CASES = [
 
 
 @pytest.mark.parametrize("case", DW_TC_CASES, ids=lambda c: c["name"])
-def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case):
+def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case, monkeypatch):
+    monkeypatch.setenv("QNNP_CUDA_DW_UMMA", "1")   # also where the router would prefer the CUDA-core kernel
     x, k, b, kw = U.conv_setup(case)
     before = gpu_lib.dw_umma_launch_count()
     got = U.run_conv(gpu_lib, case, x, k, b, kw)
