@@ -53,6 +53,8 @@ struct __align__(8) SmemCtl {
   uint64_t b_full;
   uint64_t out_full[2];  // epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
   uint64_t out_free[2];  // store thread -> epilogue pair: the staging buffer may be overwritten
+  uint64_t raw_full[2];  // raw-row staging (3x3x3 stem loader): bulk copy landed / the 128 loader threads are done with it
+  uint64_t raw_empty[2];
   uint32_t tmem_base;
 };
 
@@ -200,8 +202,63 @@ __device__ __forceinline__ void run9_load(const uint8_t* src, uint32_t (&w)[3]) 
   w[2] = __ldg(base + 2);
 }
 
-__device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid) {
-  constexpr int NB = 4;  // pixels (sub-tiles) in flight per thread
+// Raw-row staging for the run loader: the input rows an item needs are one or two CONTIGUOUS byte ranges of the NHWC
+// tensor (an item may end in one image and continue in the next), so thread 0 fetches them with bulk copies and the 128
+// loader threads then build the K rows from shared memory instead of waiting on ~200 scattered global loads each.
+struct RawSeg {
+  const uint8_t* g;   // 16-byte aligned start of the copy
+  uint32_t bytes;     // multiple of 16
+  uint32_t soff;      // offset of the copy inside the raw buffer
+  int n, iy_lo;       // image and first input row it covers
+  uint32_t delta;     // bytes between the aligned start and the first byte of row iy_lo
+};
+
+__device__ __forceinline__ int raw_segments(const IgemmParams& p, const Item& it, RawSeg (&seg)[2]) {
+  const long long m_end = min(it.m0 + (long long) it.mt_eff * kTileM, p.M);
+  const uint32_t ma = (uint32_t) it.m0, mb = (uint32_t) (m_end - 1);
+  const uint32_t ta = ma / (uint32_t) p.out_w, tb = mb / (uint32_t) p.out_w;
+  const int na = (int) (ta / (uint32_t) p.out_h), nb = (int) (tb / (uint32_t) p.out_h);
+  const int oya = (int) (ta - (uint32_t) na * p.out_h), oyb = (int) (tb - (uint32_t) nb * p.out_h);
+  const size_t row_bytes = (size_t) p.in_w * 3;
+  const uint8_t* tensor_end = p.in + (size_t) p.raw_batch * p.in_h * row_bytes;
+  const int nseg = na == nb ? 1 : 2;
+  uint32_t soff = 0;
+  for (int s = 0; s < nseg; s++) {
+    const int n = s == 0 ? na : nb;
+    int lo = (s == 0 ? oya * p.stride_h - p.pad_top : 0);
+    int hi = (s == nseg - 1 ? oyb * p.stride_h - p.pad_top + (p.kh - 1) * p.dil_h : p.in_h - 1);
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > p.in_h - 1 ? p.in_h - 1 : hi;
+    const uint8_t* g0 = p.in + ((size_t) n * p.in_h + lo) * row_bytes;
+    const uint8_t* g1 = p.in + ((size_t) n * p.in_h + hi + 1) * row_bytes;
+    const uint8_t* ga = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(g0) & ~(uintptr_t) 15);
+    const uint8_t* gb = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(g1) + 15) & ~(uintptr_t) 15);
+    gb = gb > tensor_end ? tensor_end : gb;  // (tensor base and size are multiples of 16: host-checked)
+    seg[s].g = ga;
+    seg[s].bytes = hi >= lo ? (uint32_t) (gb - ga) : 0u;
+    seg[s].soff = soff;
+    seg[s].n = n;
+    seg[s].iy_lo = lo;
+    seg[s].delta = (uint32_t) (g0 - ga);
+    soff += seg[s].bytes;
+  }
+  return nseg;
+}
+
+__device__ __forceinline__ void run9_load_smem(uint32_t saddr, uint32_t (&w)[3]) {
+  const uint32_t base = saddr & ~3u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[0]) : "r"(base));
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[1]) : "r"(base + 4));
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[2]) : "r"(base + 8));
+}
+
+// RAW: the 9-byte runs come from the raw-row staging buffer at shared address `raw` (see raw_segments) instead of global
+// raw_n0 / raw_b0 / raw_b1: image of the first staged range and, for both ranges, the shared address of the (virtual)
+// byte (row 0, column 0) of their image — so a run's address is one multiply-add away
+template <bool RAW>
+__device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid, int raw_n0,
+                                                 uint32_t raw_b0, uint32_t raw_b1) {
+  constexpr int NB = RAW ? 2 : 4;  // pixels (sub-tiles) in flight per thread (shared-memory reads need less cover)
   const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
   for (int j0 = 0; j0 < it.mt_eff; j0 += NB) {
     uint32_t w[NB][3][3];
@@ -227,7 +284,13 @@ __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Ite
         const uint8_t* src = img + (size_t) (rowok ? iy : 0) * p.in_w * 3;
         info[jj] |= (((uint32_t) reinterpret_cast<uintptr_t>(src) & 3u) | (st << 2)) << (4 * ky);
         if (st == 0) {
-          run9_load(src, w[jj][ky]);
+          if constexpr (RAW) {
+            // same bytes, staged: shared address = buffer + copy offset + (row, column) inside the copied rows; the
+            // copy starts 16-byte aligned in both spaces, so the low address bits (the funnel-shift amount) agree
+            run9_load_smem(((int) n == raw_n0 ? raw_b0 : raw_b1) + (uint32_t) (iy * p.in_w + ix0) * 3u, w[jj][ky]);
+          } else {
+            run9_load(src, w[jj][ky]);
+          }
         } else {
           w[jj][ky][0] = w[jj][ky][1] = w[jj][ky][2] = fill;
         }
@@ -291,6 +354,7 @@ __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Ite
 // no-swizzle UMMA operand image of a sub-tile — and signals the stage barrier with its byte count.  No per-lane
 // address arithmetic, rows beyond M and chunks beyond K are zero-filled by the hardware.
 constexpr int kVecTma = 32;  // value of the VEC template parameter that selects this loader
+constexpr int kVecRaw9 = 2;  // 3x3x3 run loader fed from bulk-copied raw rows (load_a_conv_run9<true>)
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
@@ -515,6 +579,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&ctl.out_full[s]), kEpiPairThreads);
       mbar_init(smem_u32(&ctl.out_free[s]), 1);
+      mbar_init(smem_u32(&ctl.raw_full[s]), 1);
+      mbar_init(smem_u32(&ctl.raw_empty[s]), kLoadThreads);
     }
     fence_mbar_init();
   }
@@ -545,6 +611,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     int stage = 0;
     uint32_t phase = 0;
+    [[maybe_unused]] uint32_t ri = 0;  // items seen (raw staging: buffer = ri & 1, its use count = ri >> 1)
+    [[maybe_unused]] const uint32_t raw0 = smem_base + (uint32_t) p.smem_raw_off;
+    [[maybe_unused]] auto issue_raw = [&](long long item, uint32_t idx) {  // thread 0: fetch the rows of `item`
+      const Item nx = decode_item(p, item);
+      RawSeg sg[2];
+      const int ns = raw_segments(p, nx, sg);
+      const uint32_t b = idx & 1, k = idx >> 1;
+      mbar_wait(smem_u32(&ctl.raw_empty[b]), (k & 1) ^ 1);
+      const uint32_t bar = smem_u32(&ctl.raw_full[b]);
+      mbar_arrive_expect_tx(bar, sg[0].bytes + (ns > 1 ? sg[1].bytes : 0u));
+      for (int s = 0; s < ns; s++)
+        if (sg[s].bytes != 0) bulk_g2s(raw0 + b * (uint32_t) p.raw_cap + sg[s].soff, sg[s].g, sg[s].bytes, bar);
+    };
+    if constexpr (VEC == kVecRaw9) {
+      if (ltid == 0 && first < p.total_items) issue_raw(first, 0);
+    }
     for (long long item = first; item < p.total_items; item += step) {
       const Item it = decode_item(p, item);
       for (int ks = 0; ks < p.k_stages; ks++) {
@@ -564,7 +646,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else if constexpr (MODE == kModeGemm) {
           load_a_gemm<VEC>(p, it, ks, a_stage, ltid);
         } else if constexpr (VEC == 0) {
-          load_a_conv_run9(p, it, a_stage, ltid);  // K = 27 fits one stage
+          load_a_conv_run9<false>(p, it, a_stage, ltid, 0, 0u, 0u);  // K = 27 fits one stage
+        } else if constexpr (VEC == kVecRaw9) {
+          if (ltid == 0 && item + step < p.total_items) issue_raw(item + step, ri + 1);  // prefetch the next item's rows
+          RawSeg sg[2];
+          const int ns = raw_segments(p, it, sg);
+          const uint32_t rb = raw0 + (ri & 1) * (uint32_t) p.raw_cap;
+          const uint32_t b0 = rb + sg[0].soff + sg[0].delta - (uint32_t) (sg[0].iy_lo * p.in_w) * 3u;
+          const uint32_t b1 = ns > 1 ? rb + sg[1].soff + sg[1].delta - (uint32_t) (sg[1].iy_lo * p.in_w) * 3u : b0;
+          mbar_wait(smem_u32(&ctl.raw_full[ri & 1]), (ri >> 1) & 1);
+          load_a_conv_run9<true>(p, it, a_stage, ltid, sg[0].n, b0, b1);
+          mbar_arrive(smem_u32(&ctl.raw_empty[ri & 1]));
+          ri++;
         } else {
           load_a_conv<VEC>(p, it, ks, a_stage, ltid);
         }
@@ -768,6 +861,7 @@ cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void*
       case 8: return launch_one<kModeConv, 8>(p, tmap, grid, stream);
       case 4: return launch_one<kModeConv, 4>(p, tmap, grid, stream);
       case 0: return launch_one<kModeConv, 0>(p, tmap, grid, stream);  // 9-byte row runs (3x3, 3 channels)
+      case 2: return launch_one<kModeConv, kVecRaw9>(p, tmap, grid, stream);  // ... from bulk-staged raw rows
       default: return launch_one<kModeConv, 1>(p, tmap, grid, stream);
     }
   }

@@ -769,6 +769,26 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
           op->in_stride == 3 && op->k_stages == 1 && op->in_w >= 3 && ((uintptr_t) in % 4) == 0 &&
           (M * 0 + op->batch * op->in_h * op->in_w * 3) % 4 == 0 && getenv("QNNP_CUDA_NO_RUN9") == nullptr)
         vec = 0;
+      // ... and those runs are read from bulk-staged raw input rows when the tensor can be bulk-copied (16-byte aligned
+      // base and size) and an item never spans more than two images; the A ring gives up stages for the two raw buffers
+      if (vec == 0 && ((uintptr_t) in % 16) == 0 && ((size_t) op->batch * op->in_h * op->in_w * 3) % 16 == 0 &&
+          (size_t) op->out_h * op->out_w >= (size_t) op->mt * q8::kTileM && getenv("QNNP_CUDA_NO_RAW9") == nullptr) {
+        const int rows_out = (int) ((op->mt * q8::kTileM + op->out_w - 2) / op->out_w) + 1;
+        const int rows_in = (rows_out + 1) * (int) op->stride_h + 2 * (int) ((op->kh - 1) * op->dil_h + 1);
+        const int raw_cap = (int) round_up((size_t) rows_in * op->in_w * 3 + 64, 128);
+        int stages = p.num_stages;
+        const int fixed = p.smem_a_off + 2 * p.staging_bytes + 1024 + 2 * raw_cap;
+        while (stages > 3 && fixed + stages * p.stage_bytes > g_lib.max_smem_optin - kCtlReserve) stages--;
+        if (fixed + stages * p.stage_bytes <= g_lib.max_smem_optin - kCtlReserve) {
+          p.num_stages = stages;
+          p.smem_stage_off = p.smem_a_off + stages * p.stage_bytes;
+          p.smem_raw_off = p.smem_stage_off + 2 * p.staging_bytes;
+          p.raw_cap = raw_cap;
+          p.raw_batch = (int) op->batch;
+          p.smem_total = p.smem_raw_off + 2 * raw_cap + 1024;
+          vec = 2;
+        }
+      }
       // 1x1 / FC with 16-byte aligned rows: the TMA loads the activation tiles
       alignas(64) CUtensorMap tmap;
       const void* tmap_ptr = nullptr;

@@ -76,6 +76,22 @@ def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case, monkeypatch):
     U.assert_same_bytes(got, U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
 
 
+# 3x3 over 3 dense channels (the MobileNetV2 stem shape class): run loader fed from bulk-staged raw rows; the items
+# of these cases straddle image boundaries and rows that are not multiples of 16 bytes
+STEM_CASES = [
+    CS.conv_case("stem_72_b5", 5, 72, 72, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
+    CS.conv_case("stem_70x74_b4", 4, 70, 74, 1, 3, 24, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
+    CS.conv_case("stem_s1_40_b4", 4, 40, 40, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
+    CS.conv_case("stem_nopad_66_b4", 4, 66, 66, 1, 3, 32, ks=(3, 3), stride=(2, 2)),
+]
+
+
+@pytest.mark.parametrize("case", STEM_CASES, ids=lambda c: c["name"])
+def test_stem_conv_raw_row_loader(gpu_lib, oracle_c, case):
+    x, k, b, kw = U.conv_setup(case)
+    U.assert_same_bytes(U.run_conv(gpu_lib, case, x, k, b, kw), U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
+
+
 # ---- q8gemm through the fully-connected operator ------------------------------------------------------
 @pytest.mark.parametrize("case", CS.GEMM_UKERNEL_CASES, ids=lambda c: c["name"])
 def test_q8gemm(gpu_lib, golden, case):
