@@ -111,19 +111,22 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
 template <int RQ, int NB>
 __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t taddr, const int32_t* bias, uint8_t* dst, bool valid,
                                               bool last, uint32_t tmem_empty_bar) {
+  // order: start the (asynchronous) TMEM load, fetch the bias words while it is in flight, then wait — the wait is a
+  // compiler barrier for memory operations, so the bias loads must be issued before it
+  int32_t v[16];
+  int32_t w[NB == 32 ? 32 : 1];
+  if constexpr (NB == 32) {
+    tmem_ld32(taddr, w);
+  } else {
+    tmem_ld16(taddr, v);
+  }
   int4 b[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) b[t] = __ldg(reinterpret_cast<const int4*>(bias) + t);
-  int32_t v[16];
+  tmem_ld_wait();
   if constexpr (NB == 32) {
-    int32_t w[32];
-    tmem_ld32(taddr, w);
-    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = w[i] + w[16 + i];  // (w - kzp) = A + B: the two operand halves
-  } else {
-    tmem_ld16(taddr, v);
-    tmem_ld_wait();
   }
   if (last) {  // this warp has read everything it needs from the accumulator stage
     tc_fence_before_sync();
@@ -150,14 +153,13 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
   if (valid) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// UMMA-issuing role of warp kMmaWarp + W: lane 0 alone runs the loop.  (Keeping the whole warp in the loop and
+// UMMA-issuing role of warp kMmaWarp + w: lane 0 alone runs the loop.  (Keeping the whole warp in the loop and
 // predicating only the tcgen05 instructions is far worse: nvcc wraps every tcgen05.mma in an elect/broadcast loop that
 // then iterates once per ACTIVE lane — measured 3x slower.)
-template <int NB, int W>
-__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t smem_base, uint32_t tmem_base, int lane,
+template <int NB>
+__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t smem_base, uint32_t tmem_base, int lane, int w,
                                          uint32_t first, uint32_t step, uint32_t total) {
     if (lane == 0) {
-      constexpr int w = W;
       const uint32_t tmem_u = tmem_base;
       const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
       uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
@@ -264,12 +266,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     // four busy epilogue warps, so one thread manages only one UMMA per ~100 cycles (measured).  Four warps — one per
     // sub-partition — issue concurrently; warp w owns the units w, w+4, ... of every item.  (Eight issuing warps were
     // measured 3x SLOWER than four.)
-    switch (warp - kMmaWarp) {
-      case 0: mma_role<NB, 0>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
-      case 1: mma_role<NB, 1>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
-      case 2: mma_role<NB, 2>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
-      default: mma_role<NB, 3>(p, ctl, smem_base, tmem_base, lane, first, step, total); break;
-    }
+    // (one copy of the loop for all four: per-warp template instances quadruple the code and were measured 2.3x slower,
+    // presumably instruction-cache misses)
+    mma_role<NB>(p, ctl, smem_base, tmem_base, lane, warp - kMmaWarp, first, step, total);
   } else {
     // ===================================== epilogue (16 warps) =====================================
     const int q = warp & 3, h = warp >> 2;
