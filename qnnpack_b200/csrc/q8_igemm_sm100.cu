@@ -44,6 +44,7 @@ constexpr int kStoreWarp = kLoadWarp0 + kLoadWarps;       // lanes 0/1: bulk-sto
 constexpr int kThreads = (kStoreWarp + 1) * 32;           // 704
 constexpr int kEpiPairThreads = 256;
 constexpr int kTmemCols = 512;
+constexpr int kMaxRawBufs = 4;
 
 struct __align__(8) SmemCtl {
   uint64_t full[kMaxStages];
@@ -53,8 +54,8 @@ struct __align__(8) SmemCtl {
   uint64_t b_full;
   uint64_t out_full[2];  // epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
   uint64_t out_free[2];  // store thread -> epilogue pair: the staging buffer may be overwritten
-  uint64_t raw_full[2];  // raw-row staging (3x3x3 stem loader): bulk copy landed / the 128 loader threads are done with it
-  uint64_t raw_empty[2];
+  uint64_t raw_full[kMaxRawBufs];  // raw-row staging (3x3x3 stem loader): bulk copies landed / 128 loader threads done
+  uint64_t raw_empty[kMaxRawBufs];
   uint32_t tmem_base;
 };
 
@@ -362,6 +363,70 @@ __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Ite
   }
 }
 
+// The same K rows built from the raw-row staging buffer, branch-free.  Every run is read as 12 aligned bytes at its
+// nominal address even when it starts left of the row or ends right of it (the neighbouring bytes are readable shared
+// memory); the pixels of the run that are padding are then overwritten with the input zero point through byte masks,
+// and a run whose whole row is padding is replaced likewise.  (The global-memory variant above needs an explicit
+// byte-wise edge path for that; with a warp of consecutive pixels almost every third warp took it.)
+__device__ __forceinline__ void load_a_conv_run9_raw(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid, int raw_n0,
+                                                     uint32_t raw_b0, uint32_t raw_b1, uint32_t raw_safe) {
+  const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
+  uint32_t cn;
+  int coy, cox;
+  {
+    const uint32_t mu = (uint32_t) (it.m0 + ltid);  // M < 2^31 (host-checked)
+    const uint32_t t = mu / (uint32_t) p.out_w;
+    cox = (int) (mu - t * (uint32_t) p.out_w);
+    cn = t / (uint32_t) p.out_h;
+    coy = (int) (t - cn * (uint32_t) p.out_h);
+  }
+  const int row_pitch = p.in_w * 3;
+#pragma unroll 2
+  for (int j = 0; j < it.mt_eff; j++) {
+    const bool live = it.m0 + (long long) j * kTileM + ltid < p.M;
+    const int ix0 = cox * p.stride_w - p.pad_left, iy0 = coy * p.stride_h - p.pad_top;
+    // byte masks of the padded pixels of a run: pixel i (bytes 3i..3i+2) is padding if ix0 + i is outside [0, in_w)
+    const int lo = ix0 < 0 ? -ix0 : 0, hi = ix0 + 3 - p.in_w > 0 ? ix0 + 3 - p.in_w : 0;
+    uint32_t m0 = lo == 0 ? 0u : (lo == 1 ? 0x00FFFFFFu : 0xFFFFFFFFu);
+    uint32_t m1 = lo >= 2 ? (lo == 2 ? 0x0000FFFFu : 0xFFFFFFFFu) : 0u;
+    uint32_t m2 = lo >= 3 ? 0xFFu : 0u;
+    if (hi >= 1) m1 |= 0xFFFF0000u, m2 |= 0xFFu;
+    if (hi >= 2) m0 |= 0xFF000000u, m1 = 0xFFFFFFFFu;
+    if (hi >= 3) m0 = 0xFFFFFFFFu;
+    const uint32_t base = ((int) cn == raw_n0 ? raw_b0 : raw_b1) + (uint32_t) (iy0 * row_pitch + ix0 * 3);
+    uint32_t r[3][3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      const int iy = iy0 + ky * p.dil_h;
+      const bool rowok = live && (unsigned) iy < (unsigned) p.in_h;
+      const uint32_t a = base + (uint32_t) (ky * p.dil_h * row_pitch);
+      uint32_t w[3];
+      run9_load_smem(rowok ? a : raw_safe, w);  // (any readable address when the row is padding)
+      const uint32_t sh = (a & 3u) * 8;
+      const uint32_t r0 = __funnelshift_r(w[0], w[1], sh), r1 = __funnelshift_r(w[1], w[2], sh), r2 = w[2] >> sh;
+      const uint32_t k0 = rowok ? m0 : 0xFFFFFFFFu, k1 = rowok ? m1 : 0xFFFFFFFFu, k2 = rowok ? m2 : 0xFFu;
+      r[ky][0] = (r0 & ~k0) | (fill & k0);
+      r[ky][1] = (r1 & ~k1) | (fill & k1);
+      r[ky][2] = ((r2 & ~k2) | (fill & k2)) & 0xFFu;
+    }
+    // K row: bytes [0,9) = ky 0, [9,18) = ky 1, [18,27) = ky 2, [27,32) = padding (zero weights)
+    const uint32_t k0 = r[0][0], k1 = r[0][1];
+    const uint32_t k2 = r[0][2] | (r[1][0] << 8);
+    const uint32_t k3 = __funnelshift_r(r[1][0], r[1][1], 24);
+    const uint32_t k4 = (r[1][1] >> 24) | (r[1][2] << 8) | (r[2][0] << 16);
+    const uint32_t k5 = __funnelshift_r(r[2][0], r[2][1], 16);
+    const uint32_t k6 = (r[2][1] >> 16) | (r[2][2] << 16);
+    const uint32_t d = a_stage + (uint32_t) (j * p.skc) * kChunkBytes + (uint32_t) ltid * 16;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(k0), "r"(k1), "r"(k2), "r"(k3) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + kChunkBytes), "r"(k4), "r"(k5), "r"(k6), "r"(0u) : "memory");
+    cox += kTileM;  // the same row of the next sub-tile is 128 pixels further along the NHW order
+    while (cox >= p.out_w) {
+      cox -= p.out_w;
+      if (++coy == p.out_h) coy = 0, cn++;
+    }
+  }
+}
+
 // 1x1 / fully-connected through the TMA: the activation matrix is described once (host side) as a 3-D tensor
 // {16 bytes of K, M rows, K/16 chunks}; ONE instruction then lands a [chunks][128 rows][16 B] box — exactly the
 // no-swizzle UMMA operand image of a sub-tile — and signals the stage barrier with its byte count.  No per-lane
@@ -592,6 +657,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&ctl.out_full[s]), kEpiPairThreads);
       mbar_init(smem_u32(&ctl.out_free[s]), 1);
+    }
+    for (int s = 0; s < kMaxRawBufs; s++) {
       mbar_init(smem_u32(&ctl.raw_full[s]), 1);
       mbar_init(smem_u32(&ctl.raw_empty[s]), kLoadThreads);
     }
@@ -624,21 +691,33 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     int stage = 0;
     uint32_t phase = 0;
-    [[maybe_unused]] uint32_t ri = 0;  // items seen (raw staging: buffer = ri & 1, its use count = ri >> 1)
+    // raw staging ring: buffer rb (use parity rpar) holds the rows of the current item; thread 0 keeps raw_bufs - 1
+    // items of rows in flight ahead of the one being transformed (a single outstanding copy was measured to leave the
+    // loader warps waiting ~95% of the time)
+    [[maybe_unused]] int rb = 0, pb = 0;           // consumer / producer buffer index
+    [[maybe_unused]] uint32_t rpar = 0, ppar = 0;  // their use parities
+    [[maybe_unused]] long long pitem = first;      // next item whose rows have not been requested yet
     [[maybe_unused]] const uint32_t raw0 = smem_base + (uint32_t) p.smem_raw_off;
-    [[maybe_unused]] auto issue_raw = [&](long long item, uint32_t idx) {  // thread 0: fetch the rows of `item`
-      const Item nx = decode_item(p, item);
+    [[maybe_unused]] auto issue_raw = [&]() {  // thread 0: request the rows of `pitem` into buffer pb
+      const Item nx = decode_item(p, pitem);
       RawSeg sg[2];
       const int ns = raw_segments(p, nx, sg);
-      const uint32_t b = idx & 1, k = idx >> 1;
-      mbar_wait(smem_u32(&ctl.raw_empty[b]), (k & 1) ^ 1);
-      const uint32_t bar = smem_u32(&ctl.raw_full[b]);
+      mbar_wait(smem_u32(&ctl.raw_empty[pb]), ppar ^ 1);
+      const uint32_t bar = smem_u32(&ctl.raw_full[pb]);
       mbar_arrive_expect_tx(bar, sg[0].bytes + (ns > 1 ? sg[1].bytes : 0u));
-      for (int s = 0; s < ns; s++)
-        if (sg[s].bytes != 0) bulk_g2s(raw0 + b * (uint32_t) p.raw_cap + sg[s].soff, sg[s].g, sg[s].bytes, bar);
+      for (int s = 0; s < ns; s++) {
+        // several medium copies instead of one large one: they proceed in parallel
+        for (uint32_t o = 0; o < sg[s].bytes; o += 4096) {
+          const uint32_t len = sg[s].bytes - o < 4096 ? sg[s].bytes - o : 4096;
+          bulk_g2s(raw0 + (uint32_t) pb * (uint32_t) p.raw_cap + sg[s].soff + o, sg[s].g + o, len, bar);
+        }
+      }
+      pitem += step;
+      if (++pb == p.raw_bufs) pb = 0, ppar ^= 1;
     };
     if constexpr (VEC == kVecRaw9) {
-      if (ltid == 0 && first < p.total_items) issue_raw(first, 0);
+      if (ltid == 0)
+        for (int i = 0; i < p.raw_bufs - 1 && pitem < p.total_items; i++) issue_raw();
     }
     for (long long item = first; item < p.total_items; item += step) {
       const Item it = decode_item(p, item);
@@ -661,16 +740,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else if constexpr (VEC == 0) {
           load_a_conv_run9<false>(p, it, a_stage, ltid, 0, 0u, 0u);  // K = 27 fits one stage
         } else if constexpr (VEC == kVecRaw9) {
-          if (ltid == 0 && item + step < p.total_items) issue_raw(item + step, ri + 1);  // prefetch the next item's rows
+          if (ltid == 0 && pitem < p.total_items) issue_raw();  // keep the ring of row requests full
           RawSeg sg[2];
           const int ns = raw_segments(p, it, sg);
-          const uint32_t rb = raw0 + (ri & 1) * (uint32_t) p.raw_cap;
-          const uint32_t b0 = rb + sg[0].soff + sg[0].delta - (uint32_t) (sg[0].iy_lo * p.in_w) * 3u;
-          const uint32_t b1 = ns > 1 ? rb + sg[1].soff + sg[1].delta - (uint32_t) (sg[1].iy_lo * p.in_w) * 3u : b0;
-          mbar_wait(smem_u32(&ctl.raw_full[ri & 1]), (ri >> 1) & 1);
-          load_a_conv_run9<true>(p, it, a_stage, ltid, sg[0].n, b0, b1);
-          mbar_arrive(smem_u32(&ctl.raw_empty[ri & 1]));
-          ri++;
+          const uint32_t rbase = raw0 + (uint32_t) rb * (uint32_t) p.raw_cap;
+          const uint32_t b0 = rbase + sg[0].soff + sg[0].delta - (uint32_t) (sg[0].iy_lo * p.in_w) * 3u;
+          const uint32_t b1 = ns > 1 ? rbase + sg[1].soff + sg[1].delta - (uint32_t) (sg[1].iy_lo * p.in_w) * 3u : b0;
+          mbar_wait(smem_u32(&ctl.raw_full[rb]), rpar);
+          load_a_conv_run9_raw(p, it, a_stage, ltid, sg[0].n, b0, b1, rbase);
+          mbar_arrive(smem_u32(&ctl.raw_empty[rb]));
+          if (++rb == p.raw_bufs) rb = 0, rpar ^= 1;
         } else {
           load_a_conv<VEC>(p, it, ks, a_stage, ltid);
         }

@@ -776,16 +776,21 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         const int rows_out = (int) ((op->mt * q8::kTileM + op->out_w - 2) / op->out_w) + 1;
         const int rows_in = (rows_out + 1) * (int) op->stride_h + 2 * (int) ((op->kh - 1) * op->dil_h + 1);
         const int raw_cap = (int) round_up((size_t) rows_in * op->in_w * 3 + 64, 128);
-        int stages = p.num_stages;
-        const int fixed = p.smem_a_off + 2 * p.staging_bytes + 1024 + 2 * raw_cap;
-        while (stages > 3 && fixed + stages * p.stage_bytes > g_lib.max_smem_optin - kCtlReserve) stages--;
-        if (fixed + stages * p.stage_bytes <= g_lib.max_smem_optin - kCtlReserve) {
+        // split the shared memory that the A ring had: 4 raw buffers if >= 3 A stages remain, else 3, else 2
+        int max_bufs = 4;
+        if (const char* ev = getenv("QNNP_CUDA_RAW_BUFS")) max_bufs = atoi(ev) < 2 ? 2 : (atoi(ev) > 4 ? 4 : atoi(ev));
+        for (int bufs = max_bufs; bufs >= 2 && vec == 0; bufs--) {
+          const int fixed = p.smem_a_off + 2 * p.staging_bytes + 1024 + bufs * raw_cap;
+          int stages = p.num_stages;
+          while (stages > 3 && fixed + stages * p.stage_bytes > g_lib.max_smem_optin - kCtlReserve) stages--;
+          if (fixed + stages * p.stage_bytes > g_lib.max_smem_optin - kCtlReserve) continue;
           p.num_stages = stages;
           p.smem_stage_off = p.smem_a_off + stages * p.stage_bytes;
           p.smem_raw_off = p.smem_stage_off + 2 * p.staging_bytes;
           p.raw_cap = raw_cap;
+          p.raw_bufs = bufs;
           p.raw_batch = (int) op->batch;
-          p.smem_total = p.smem_raw_off + 2 * raw_cap + 1024;
+          p.smem_total = p.smem_raw_off + bufs * raw_cap + 1024;
           vec = 2;
         }
       }
