@@ -21,26 +21,15 @@
 
 namespace q8 {
 
+// RQ 5 / 6: "U" requantisation without / with clamp; anything else: the generic run-time form
 template <int RQ>
 __device__ __forceinline__ int32_t requant_one(int32_t n, const Q8Requant& rq) {
-  if constexpr (RQ == 0) {
-    return q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
-  } else if constexpr (RQ == 1) {
-    int32_t t = q8_requant_fused_unclamped(n, rq.multiplier, rq.c_pos, rq.shift - 1);
-    t = max(t, rq.qmin);
-    return min(t, rq.qmax);
-  } else if constexpr (RQ == 5 || RQ == 6) {
+  if constexpr (RQ == 5 || RQ == 6) {
     int32_t t = q8_requant_u_unclamped((uint32_t) n ^ 0x80000000u, rq.u_m2, rq.u_k2, rq.u_sm);
     if constexpr (RQ == 6) t = min(max(t, rq.qmin), rq.qmax);
     return t;
-  } else if constexpr (RQ == 2) {
-    return q8_requant_shift0(n, rq.multiplier, rq.zero_point, rq.qmin, rq.qmax);
-  } else if constexpr (RQ == 4) {
-    int32_t t = q8_requant_fused_shift1_unclamped(n, rq.multiplier, rq.c_neg);
-    t = max(t, rq.qmin);
-    return min(t, rq.qmax);
   } else {
-    return q8_requant_exact_slow(n, rq);
+    return q8_requant(n, rq);
   }
 }
 
@@ -152,10 +141,6 @@ static cudaError_t launch_dw_rq(const DwParams& p, cudaStream_t stream) {
   const int threads = 256;
   const long long blocks = (p.total_threads + threads - 1) / threads;
   switch (p.rq_mode) {
-    case 0: q8_dwconv3x3_kernel<CV, SW, TX, 0><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
-    case 1: q8_dwconv3x3_kernel<CV, SW, TX, 1><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
-    case 2: q8_dwconv3x3_kernel<CV, SW, TX, 2><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
-    case 4: q8_dwconv3x3_kernel<CV, SW, TX, 4><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     case 5: q8_dwconv3x3_kernel<CV, SW, TX, 5><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     case 6: q8_dwconv3x3_kernel<CV, SW, TX, 6><<<(unsigned) blocks, threads, 0, stream>>>(p); break;
     default: q8_dwconv3x3_kernel<CV, SW, TX, 3><<<(unsigned) blocks, threads, 0, stream>>>(p); break;

@@ -130,8 +130,7 @@ __device__ __forceinline__ void finish_row(const DwStreamParams& p, uint8_t* oba
           };
           packed = pack_sat_u8x4(rq1(acc[x][0]), rq1(acc[x][1]), rq1(acc[x][2]), rq1(acc[x][3]));
         } else {
-          packed = pack_sat_u8x4(requant_dev<RQ>(acc[x][0], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][1], p.rq, p.shift_mul),
-                                 requant_dev<RQ>(acc[x][2], p.rq, p.shift_mul), requant_dev<RQ>(acc[x][3], p.rq, p.shift_mul));
+          packed = requant_pack4_generic(acc[x][0], acc[x][1], acc[x][2], acc[x][3], p.rq);
         }
         *reinterpret_cast<uint32_t*>(orow + (size_t) (ox0 + x) * p.out_stride) = packed;
       }
@@ -251,10 +250,6 @@ cudaError_t launch_rq(const DwStreamParams& p, cudaStream_t stream) {
   const int threads = 128;
   const unsigned blocks = (unsigned) ((p.total_threads + threads - 1) / threads);
   switch (p.rq_mode) {
-    case 0: q8_dwconv3x3_stream_kernel<S, WMODE, 0><<<blocks, threads, 0, stream>>>(p); break;
-    case 1: q8_dwconv3x3_stream_kernel<S, WMODE, 1><<<blocks, threads, 0, stream>>>(p); break;
-    case 2: q8_dwconv3x3_stream_kernel<S, WMODE, 2><<<blocks, threads, 0, stream>>>(p); break;
-    case 4: q8_dwconv3x3_stream_kernel<S, WMODE, 4><<<blocks, threads, 0, stream>>>(p); break;
     case 5: q8_dwconv3x3_stream_kernel<S, WMODE, 5><<<blocks, threads, 0, stream>>>(p); break;
     case 6: q8_dwconv3x3_stream_kernel<S, WMODE, 6><<<blocks, threads, 0, stream>>>(p); break;
     default: q8_dwconv3x3_stream_kernel<S, WMODE, 3><<<blocks, threads, 0, stream>>>(p); break;

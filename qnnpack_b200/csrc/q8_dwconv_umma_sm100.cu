@@ -135,20 +135,21 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
   uint32_t o[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) {
-    int32_t y[4];
     const int32_t bb[4] = {b[t].x, b[t].y, b[t].z, b[t].w};
+    int32_t n[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int32_t n = v[4 * t + i] + bb[i];  // for RQ 5/6 the table already carries the 2^31 offset of the "U" form
-      if constexpr (RQ == 5 || RQ == 6) {
-        int32_t r = q8_requant_u_unclamped((uint32_t) n, p.rq.u_m2, p.rq.u_k2, p.rq.u_sm);
-        if constexpr (RQ == 6) r = min(max(r, p.rq.qmin), p.rq.qmax);
-        y[i] = r;
-      } else {
-        y[i] = q8_requant(n, p.rq);
+    for (int i = 0; i < 4; i++) n[i] = v[4 * t + i] + bb[i];  // for RQ 5/6 the table already carries the 2^31 offset of "U"
+    if constexpr (RQ == 5 || RQ == 6) {
+      int32_t y[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        y[i] = q8_requant_u_unclamped((uint32_t) n[i], p.rq.u_m2, p.rq.u_k2, p.rq.u_sm);
+        if constexpr (RQ == 6) y[i] = min(max(y[i], p.rq.qmin), p.rq.qmax);
       }
+      o[t] = pack_sat_u8x4(y[0], y[1], y[2], y[3]);
+    } else {
+      o[t] = requant_pack4_generic(n[0], n[1], n[2], n[3], p.rq);
     }
-    o[t] = pack_sat_u8x4(y[0], y[1], y[2], y[3]);
   }
   if (valid) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }

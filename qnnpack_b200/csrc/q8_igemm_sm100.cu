@@ -582,9 +582,7 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
     for (int t = 0; t < W / 4; t++) w[t] = pack_sat_u8x4(rq1(v[4 * t]), rq1(v[4 * t + 1]), rq1(v[4 * t + 2]), rq1(v[4 * t + 3]));
   } else {
 #pragma unroll
-    for (int t = 0; t < W / 4; t++)  // (saturation to [0,255] is the clamp when qmin = 0, qmax = 255)
-      w[t] = pack_sat_u8x4(requant_dev<RQ>(v[4 * t], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 1], p.rq, p.shift_mul),
-                           requant_dev<RQ>(v[4 * t + 2], p.rq, p.shift_mul), requant_dev<RQ>(v[4 * t + 3], p.rq, p.shift_mul));
+    for (int t = 0; t < W / 4; t++) w[t] = requant_pack4_generic(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3], p.rq);
   }
   if (first && p.out_mode == 1) mbar_wait(e.out_free_bar, e.out_free_parity);  // the previous bulk store has left staging
   emit<W>(p, it, e, j, c0, w);
@@ -876,11 +874,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       e.out_free_bar = smem_u32(&ctl.out_free[pair]);
       e.out_free_parity = (k & 1) ^ 1;
       e.tmem_empty_bar = smem_u32(&ctl.tmem_empty[as]);
+      // two specialised epilogues ("U" requantisation without / with clamp: every layer whose accumulators are bounded,
+      // i.e. practically all) and one generic one; more instantiations only bloat the kernel (215 KB of code before)
       switch (p.rq_mode) {
-        case 0: epilogue_dispatch<0>(p, it, e, half); break;
-        case 1: epilogue_dispatch<1>(p, it, e, half); break;
-        case 2: epilogue_dispatch<2>(p, it, e, half); break;
-        case 4: epilogue_dispatch<4>(p, it, e, half); break;
         case 5: epilogue_dispatch<5>(p, it, e, half); break;
         case 6: epilogue_dispatch<6>(p, it, e, half); break;
         default: epilogue_dispatch<3>(p, it, e, half); break;

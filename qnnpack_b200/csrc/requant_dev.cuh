@@ -38,8 +38,15 @@ __device__ __forceinline__ int32_t requant_dev(int32_t n, const Q8Requant& rq, i
     y = max(y, rq.qmin);
     return min(y, rq.qmax);
   } else {
-    return q8_requant_exact_slow(n, rq);
+    return q8_requant(n, rq);  // RQ 3 = generic: picks the fused / shift-0 / shift-1 / exact form at run time
   }
+}
+
+// Generic requantise + pack of four values as ONE out-of-line function: the rarely used forms must not be inlined 32x
+// into every epilogue instance (they made up most of the kernels' ~200 KB of code).
+static __device__ __noinline__ uint32_t requant_pack4_generic(int32_t a, int32_t b, int32_t c, int32_t d, const Q8Requant& rq) {
+  const int32_t ya = q8_requant(a, rq), yb = q8_requant(b, rq), yc = q8_requant(c, rq), yd = q8_requant(d, rq);
+  return (uint32_t) ya | ((uint32_t) yb << 8) | ((uint32_t) yc << 16) | ((uint32_t) yd << 24);  // already clamped to u8
 }
 
 // host helper: 2^(33 - shift) when the final shift may run as a multiply-high, else 0
