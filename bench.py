@@ -11,13 +11,13 @@ layers, are subsets of it and are reported from the same timed region in "q8gemm
   value    images/s, whole job, inputs resident in HBM, device-timed with CUDA events, max over ranks
   e2e      the same through the same C-ABI calls but with the batch coming from pinned HOST memory and
            the logits read back to the host inside the timed region
-  roofline the dominant kernel (tcgen05 implicit GEMM): algorithmic bytes / its CUDA-event time vs the
-           measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline the dominant launch of the step: its algorithmic bytes / its CUDA-event time vs the measured HBM copy
+           bandwidth (MEASURED_PEAKS.json); traffic = DRAM bytes of that launch from the committed ncu capture
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, its own SSE2 kernels and
            operator API, pthreadpool over all host cores) on a bounded sample of the same workload
 
-Multi-GPU: one process per GPU (torchrun); the batch dimension shards, packed weights are created on
-rank 0 and broadcast once over NCCL into every rank's operators; no collective in the timed steps.
+Multi-GPU: one process per GPU (torchrun); the batch dimension shards, the model parameters live on rank 0 and
+are replicated with one NCCL broadcast, then every rank packs its own operators; no collective in the timed steps.
 """
 from __future__ import annotations
 
@@ -33,6 +33,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 4096, from the committed ncu --set full captures
+NCU_DRAM_BYTES_PER_LAUNCH = {"b2_expand": 5.695e9, "stem": 2.218e9, "b1_dw": 3.342e9, "b1_project": 2.431e9,
+                             "b2_project": 1.520e9, "b3_expand": 2.102e9, "b2_dw": 6.210e9, "b3_dw": 3.659e9}
+NCU_DRAM_SOURCE = {"b2_expand": "profiles/r1c_igemm_b2_expand.summary.txt", "stem": "profiles/r1f_stem.summary.txt",
+                   "b1_dw": "profiles/r1e_dwconv_umma_b1.summary.txt", "b1_project": "profiles/r1b_igemm_first5.summary.txt",
+                   "b2_project": "profiles/r1b_igemm_first5.summary.txt", "b3_expand": "profiles/r1b_igemm_first5.summary.txt",
+                   "b2_dw": "profiles/r1b_dwconv_first3.summary.txt", "b3_dw": "profiles/r1b_dwconv_first3.summary.txt"}
 INT8_PEAK_TOPS_NOMINAL = 4500.0  # B200 dense int8 (task statement; not in MEASURED_PEAKS.json)
 
 
@@ -294,11 +301,24 @@ def b200_main(args, rank, local_rank, world):
                              "algorithmic_gb": by / 1e9, "achieved_gbs": by / 1e6 / ms, "frac_of_hbm_peak": by / 1e6 / ms / peak_gbs,
                              "tops": ops / 1e9 / ms}
     ig = per_kernel["igemm"]
-    roofline = {"kernel": "q8_igemm_kernel (tcgen05 kind::i8 implicit GEMM, fused Q31 epilogue)", "bound": "hbm",
-                "achieved": ig["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": ig["achieved_gbs"] / peak_gbs,
-                "traffic": None, "peak_source": peak_src,
-                "note": "achieved = sum of algorithmic bytes of the %d igemm launches of a step / sum of their CUDA-event "
-                        "durations in the timed region" % ig["launches_per_step"]}
+    # roofline: the dominant LAUNCH of the step (largest CUDA-event time), with its algorithmic bytes; `traffic` is
+    # that launch's dram__bytes_read + dram__bytes_write from the committed `ncu --set full` capture (profiles/),
+    # valid for the default batch only
+    dom = max(range(nl), key=lambda i: layer_ms[i])
+    dl = stack.layers[dom]
+    kname = {"dw": "q8_dwconv3x3 (tcgen05 block-diagonal UMMA or dp4a streaming kernel, see layers[])",
+             "conv": "q8_igemm_kernel<conv> (tcgen05 kind::i8 implicit GEMM, fused Q31 epilogue)"}.get(
+                 dl.kind, "q8_igemm_kernel<gemm> (tcgen05 kind::i8, TMA loads, fused Q31 epilogue)")
+    dom_gbs = dl.algorithmic_bytes(B) / 1e6 / layer_ms[dom]
+    roofline = {"kernel": kname, "layer": dl.name, "bound": "hbm", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s",
+                "frac": dom_gbs / peak_gbs,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dl.name) if B == 4096 else None,
+                "traffic_source": NCU_DRAM_SOURCE.get(dl.name) if B == 4096 else None,
+                "algorithmic_bytes": dl.algorithmic_bytes(B), "ms": layer_ms[dom], "peak_source": peak_src,
+                "all_igemm_launches": {"achieved": ig["achieved_gbs"], "frac": ig["achieved_gbs"] / peak_gbs,
+                                       "launches_per_step": ig["launches_per_step"]},
+                "note": "achieved = algorithmic bytes of the step's slowest launch / its mean CUDA-event duration in the "
+                        "timed region; per_kernel / layers[] carry every other launch"}
     # BASELINE.json configs[1]: q8gemm sweep = the distinct 1x1 / FC shapes, each once
     seen, sw_ops, sw_ms, sweep_rows = set(), 0.0, 0.0, []
     for i, l in enumerate(stack.layers):

@@ -38,9 +38,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread may stay suspended in hardware for up to `ns` before the instruction
+// returns false (it returns as soon as the phase completes), so a waiting warp polls — and takes issue slots from the
+// warps doing the work — far less often than with the default, very short, time limit.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+#ifndef Q8_MBAR_HINT_NS
+#define Q8_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if Q8_MBAR_HINT_NS > 0
+  while (!mbar_try_wait_hint(bar, parity, Q8_MBAR_HINT_NS)) {
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 // For waiters that run far ahead of their producer (ring-slot recycling): back off between polls so that the spin
 // does not take issue slots from the warps doing the work.
