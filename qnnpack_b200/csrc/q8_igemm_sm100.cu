@@ -49,8 +49,8 @@ constexpr int kMaxRawBufs = 4;
 struct __align__(8) SmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tmem_full[kMaxAccStages];   // per item (ring over the item counter & 3): all its UMMAs have completed
-  uint64_t slot_empty[kMaxAccSlots];   // per TMEM slot: the owning pair's 256 threads have read the sub-tile
+  uint64_t tmem_full[kMaxAccStages];
+  uint64_t tmem_empty[kMaxAccStages];
   uint64_t b_full;
   uint64_t out_full[2];  // epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
   uint64_t out_free[2];  // store thread -> epilogue pair: the staging buffer may be overwritten
@@ -475,10 +475,7 @@ struct EpiCtx {
   // hand-over barriers, touched as late / as early as the data dependences allow (both waits used to sit at the top
   // of the item and showed up as the two largest stall sites of the kernel):
   uint32_t out_free_bar, out_free_parity;  // waited on right before the warp's FIRST staging write of the item
-  // TMEM ring: sub-tile j of the item lives in slot (slot0 + j) mod slots; a warp arrives on slot_empty of a sub-tile
-  // right after its LAST TMEM read of it, so the UMMA warp refills slots while later sub-tiles are still being drained
-  int slot0, slots;
-  uint32_t slot_empty_bar0;                // &ctl.slot_empty[0]
+  uint32_t tmem_empty_bar;                 // arrived on right after the warp's LAST TMEM read of the item
 };
 
 // NB output bytes (NB/4 packed words, NB = 16 or 32) of row m, columns [c0, c0+NB) of the n-tile.
@@ -531,18 +528,11 @@ __device__ __forceinline__ void emit(const IgemmParams& p, const Item& it, const
 // W (16 or 32) accumulator columns of one row: TMEM -> registers -> requantise -> pack -> store.
 // FOLDED: the accumulator already contains bias and zero-point correction (extra UMMAs); otherwise
 // ("ones" mode) the folded bias comes from smem and -kzp*rowsum from accumulator column n_tile.
-__device__ __forceinline__ uint32_t slot_of(const EpiCtx& e, int j) {
-  const int s = e.slot0 + j;
-  return (uint32_t) (s >= e.slots ? s - e.slots : s);
-}
-
-// rel_from, rel_to: after this unit's TMEM reads the warp is done with sub-tiles [rel_from, rel_to) of the item
 template <int RQ, int W, bool FOLDED>
 __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, bool first,
-                                              int rel_from, int rel_to) {
+                                              bool last) {
   int32_t v[W];
-  const uint32_t tsub = e.tlane + slot_of(e, j) * (uint32_t) p.n_mma;
-  const uint32_t taddr = tsub + c0;
+  const uint32_t taddr = e.tlane + j * p.n_mma + c0;
   if constexpr (W == 32) {
     tmem_ld32(taddr, v);
   } else {
@@ -550,12 +540,12 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
   }
   int32_t rowsum = 0;
   if constexpr (!FOLDED) {
-    if (p.has_corr) tmem_ld1(tsub + p.n_tile, rowsum);
+    if (p.has_corr) tmem_ld1(e.tlane + j * p.n_mma + p.n_tile, rowsum);
   }
   tmem_ld_wait();
-  if (rel_to > rel_from) {  // sub-tiles this warp will not read again: their slots may be refilled
+  if (last) {  // the accumulator stage is drained as far as this warp is concerned: let the UMMA warp refill it now
     tc_fence_before_sync();
-    for (int s = rel_from; s < rel_to; s++) mbar_arrive(e.slot_empty_bar0 + slot_of(e, s) * 8u);
+    mbar_arrive(e.tmem_empty_bar);
   }
   if (p.dbg_acc != nullptr) {  // bring-up aid; v[] is only indexed with constants, so it stays in registers
     int32_t* d = p.dbg_acc + (((size_t) e.item * p.mt + j) * kTileM + e.row) * p.n_mma;
@@ -607,28 +597,22 @@ __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& 
   const int per_sub = full + ((p.n_tile % W) ? 1 : 0);
   const int units = it.mt_eff * per_sub;
   int j = half / per_sub, c = half - j * per_sub;
-  int rel = 0;  // sub-tiles of this item whose slots this warp has released so far (all p.mt are released, used or not)
-  if (half >= units) {  // nothing to read for this warp (tail item): release everything right away
+  if (half >= units) {  // nothing to read for this warp (tail item): release the stage right away
     tc_fence_before_sync();
-    for (int s = 0; s < p.mt; s++) mbar_arrive(e.slot_empty_bar0 + slot_of(e, s) * 8u);
+    mbar_arrive(e.tmem_empty_bar);
   }
   for (int u = half; u < units; u += 2) {
-    const bool first = u == half;
-    // where does this warp's next unit lie?  Leaving sub-tile j (or the item) releases every slot up to there.
-    int cn = c + 2, jn = j;
-    while (cn >= per_sub) {
-      cn -= per_sub;
-      ++jn;
-    }
-    const int rel_to = (u + 2 >= units) ? p.mt : jn;  // jn == j: stays in this sub-tile, nothing to release
+    const bool first = u == half, last = u + 2 >= units;
     if (c < full) {
-      epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W, first, rel, rel_to);
+      epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W, first, last);
     } else {
-      epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W, first, rel, rel_to);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
+      epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W, first, last);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
     }
-    rel = rel_to > rel ? rel_to : rel;
-    c = cn;
-    j = jn;
+    c += 2;
+    while (c >= per_sub) {
+      c -= per_sub;
+      ++j;
+    }
   }
 }
 
@@ -663,8 +647,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(smem_u32(&ctl.full[s]), VEC == kVecTma ? (p.b_resident ? 1 : 1 + kLoadThreads) : kLoadThreads);
       mbar_init(smem_u32(&ctl.empty[s]), 1);
     }
-    for (int s = 0; s < kMaxAccStages; s++) mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
-    for (int s = 0; s < kMaxAccSlots; s++) mbar_init(smem_u32(&ctl.slot_empty[s]), kEpiPairThreads);
+    for (int s = 0; s < kMaxAccStages; s++) {
+      mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
+      mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiPairThreads);
+    }
     mbar_init(smem_u32(&ctl.b_full), kLoadThreads);
     for (int s = 0; s < 2; s++) {
       mbar_init(smem_u32(&ctl.out_full[s]), kEpiPairThreads);
@@ -799,23 +785,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       int stage = 0;
       uint32_t phase = 0;
-      // TMEM ring of acc_slots sub-tile accumulators: this item takes the next mt slots; a slot is reused as soon as the
-      // epilogue has drained the sub-tile that was in it, so the UMMAs run up to acc_slots / mt items ahead
-      int slot = 0;            // first slot of the item
-      uint32_t lap = 0;        // parity of the number of completed trips around the ring (at `slot`)
-      uint32_t li = 0;         // item counter of this CTA (tmem_full ring index = li & 3)
-      auto dcol = [&](int j) -> uint32_t {  // TMEM column of the item's sub-tile j
-        const int s = slot + j;
-        return tmem_base + (uint32_t) (s >= p.acc_slots ? s - p.acc_slots : s) * (uint32_t) p.n_mma;
-      };
-      for (long long item = first; item < p.total_items; item += step, li++) {
+      int as = -1;             // accumulator stage of the item: round-robin over the 2..4 TMEM stages, so the UMMAs
+      uint32_t as_phase = 1;   // of the next items run while the epilogue still drains earlier ones
+      for (long long item = first; item < p.total_items; item += step) {
         const Item it = decode_item(p, item);
-        for (int j = 0; j < p.mt; j++) {
-          const int s = slot + j;
-          const bool wrapped = s >= p.acc_slots;
-          mbar_wait(smem_u32(&ctl.slot_empty[wrapped ? s - p.acc_slots : s]), (lap ^ (wrapped ? 1u : 0u)) ^ 1);
-        }
+        if (++as == p.acc_stages) as = 0;
+        as_phase ^= (as == 0);
+        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
         tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         // base of this (group, n_tile)'s resident block: [B1: nkc][B2 full: 2][B2 tail: 2][bias digits: 2 per step]
         const uint32_t blk = b_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.blk_chunks) * b_lbo;
         for (int ks = 0; ks < p.k_stages; ks++) {
@@ -833,22 +811,22 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int t = 0; t < p.bias_steps; t++) {
               const uint64_t ad = umma_desc_kmajor_noswizzle(a_const, kChunkBytes, 128);
               const uint64_t bd = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo, b_lbo, 128);
-              for (int j = 0; j < it.mt_eff; j++) umma_i8(dcol(j), ad, bd, idesc_us, t != 0 ? 1u : 0u);
+              for (int j = 0; j < it.mt_eff; j++) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
             }
           }
           for (int c = 0; c < cs; c += 2) {
             const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
             const uint64_t bd = umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128);
             for (int j = 0; j < it.mt_eff; j++)
-              umma_i8(dcol(j), umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128), bd, idesc_main,
-                      acc);
+              umma_i8(d_tmem + j * p.n_mma, umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128),
+                      bd, idesc_main, acc);
             if (p.has_b2) {
               // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
               const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
               const uint64_t b2 = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo, b_lbo, 128);
               for (int j = 0; j < it.mt_eff; j++)
-                umma_i8(dcol(j), umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128), b2, idesc_us,
-                        1u);
+                umma_i8(d_tmem + j * p.n_mma,
+                        umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128), b2, idesc_us, 1u);
             }
           }
           umma_commit(smem_u32(&ctl.empty[stage]));
@@ -857,9 +835,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             phase ^= 1;
           }
         }
-        umma_commit(smem_u32(&ctl.tmem_full[li & 3]));
-        slot += p.mt;
-        if (slot >= p.acc_slots) slot -= p.acc_slots, lap ^= 1;
+        umma_commit(smem_u32(&ctl.tmem_full[as]));
       }
     }
   } else if (warp < kEpiWarps) {
@@ -872,20 +848,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int lane = tid & 31;
     const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
     mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem ("ones" mode reads them)
-    uint32_t li = (uint32_t) pair;             // this CTA's item counter (the pairs alternate)
-    int slot0 = (pair * p.mt) % p.acc_slots;   // first TMEM slot of the item
-    uint32_t k = ~0u;                          // this pair's item counter
-    for (long long item = first + pair * step; item < p.total_items; item += 2 * step, li += 2) {
+    int as = pair - 2;        // accumulator stage = (local item index) mod acc_stages, tracked without divisions
+    uint32_t as_phase = 0;    // = ((local item index) / acc_stages) & 1
+    uint32_t k = ~0u;         // this pair's item counter
+    for (long long item = first + pair * step; item < p.total_items; item += 2 * step) {
       const Item it = decode_item(p, item);
       k++;
+      as += 2;
+      if (as >= p.acc_stages) {
+        as -= p.acc_stages;
+        as_phase ^= 1;
+      }
       const bool bulk = p.out_mode == 1 && (it.m0 + (long long) it.mt_eff * kTileM <= p.M);
-      mbar_wait(smem_u32(&ctl.tmem_full[li & 3]), (li >> 2) & 1);
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
       tc_fence_after_sync();
       EpiCtx e;
-      e.tlane = tmem_base + ((uint32_t) (q * 32) << 16);
-      e.slot0 = slot0;
-      e.slots = p.acc_slots;
-      e.slot_empty_bar0 = smem_u32(&ctl.slot_empty[0]);
+      e.tlane = tmem_base + as * p.acc_stride + ((uint32_t) (q * 32) << 16);
       e.bias_base = bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4;
       e.staging = staging;
       e.obase = p.out + (size_t) it.g * p.goc + (size_t) it.nt * p.n_tile;
@@ -895,6 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       e.bulk = bulk;
       e.out_free_bar = smem_u32(&ctl.out_free[pair]);
       e.out_free_parity = (k & 1) ^ 1;
+      e.tmem_empty_bar = smem_u32(&ctl.tmem_empty[as]);
       // two specialised epilogues ("U" requantisation without / with clamp: every layer whose accumulators are bounded,
       // i.e. practically all) and one generic one; more instantiations only bloat the kernel (215 KB of code before)
       switch (p.rq_mode) {
@@ -906,8 +885,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         fence_proxy_async_smem();  // staging writes (generic proxy) -> bulk copy (async proxy)
         mbar_arrive(smem_u32(&ctl.out_full[pair]));
       }
-      slot0 += 2 * p.mt;  // the other pair's item sits in between
-      while (slot0 >= p.acc_slots) slot0 -= p.acc_slots;
     }
   } else if (warp == kStoreWarp) {
     // ===================================== output stores =====================================

@@ -13,8 +13,7 @@ constexpr int kMaxNMma = 256;             // UMMA N limit; also the TMEM column 
 constexpr int kOnesCols = 16;             // extra B rows: row 0 of the block is all-ones -> per-row sum of A
 constexpr int kMaxNTile = kMaxNMma - kOnesCols;
 constexpr int kMaxSubTiles = 8;
-constexpr int kMaxAccStages = 4;          // items whose accumulators may be complete but not yet drained (tmem_full ring)
-constexpr int kMaxAccSlots = 16;          // TMEM ring: slots of n_mma columns, one per 128-row sub-tile
+constexpr int kMaxAccStages = 4;          // TMEM accumulator stages (512 columns / (mt * n_mma), at most 4)           // 128-row sub-tiles per work item (they share one TMEM stage)
 
 enum IgemmMode : int { kModeGemm = 0, kModeConv = 1 };
 
@@ -41,8 +40,8 @@ struct IgemmParams {
   int skc;        // chunks per pipeline stage, even
   int k_stages;   // ceil(nkc / skc)
   int mt;         // 128-row sub-tiles per work item
-  int acc_slots;  // TMEM ring: slots of n_mma columns (one sub-tile each); an item takes mt consecutive slots.
-                  // min(512 / n_mma, 4 * mt, 16): the UMMA warp runs up to acc_slots / mt items ahead of the epilogue
+  int acc_stages; // TMEM accumulator stages in use (2..4)
+  int acc_stride; // TMEM columns per accumulator stage (mt * n_mma)
   int n_tiles, n_tile, n_mma;
   int has_corr;   // "ones" mode only: B carries the ones block and the epilogue applies  - kzp * rowsum
   // "folded" mode: bias and zero-point correction are accumulated by extra UMMAs, the epilogue only requantises

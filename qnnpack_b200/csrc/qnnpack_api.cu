@@ -720,13 +720,12 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.M = (long long) M;
       p.m_tiles = (long long) ceil_div(M, q8::kTileM);
       p.m_super = (long long) ceil_div((size_t) p.m_tiles, (size_t) op->mt);
-      // TMEM ring: slots of n_mma columns; at most 4 items' worth (the tmem_full ring has 4 entries) and 16 slots
-      p.acc_slots = 512 / op->n_mma;
-      if (p.acc_slots > 4 * op->mt) p.acc_slots = 4 * op->mt;
-      if (p.acc_slots > q8::kMaxAccSlots) p.acc_slots = q8::kMaxAccSlots;
-      if (const char* e = getenv("QNNP_CUDA_ACC_SLOTS")) {  // experiments: e.g. 2 * mt reproduces two whole-item stages
+      p.acc_stride = op->mt * op->n_mma;
+      p.acc_stages = 512 / p.acc_stride;
+      if (p.acc_stages > q8::kMaxAccStages) p.acc_stages = q8::kMaxAccStages;
+      if (const char* e = getenv("QNNP_CUDA_ACC_STAGES")) {
         const int v = atoi(e);
-        if (v >= 2 * op->mt && v <= p.acc_slots) p.acc_slots = v;
+        if (v >= 2 && v <= p.acc_stages) p.acc_stages = v;
       }
       p.total_items = (long long) op->groups * p.m_super * op->n_tiles;
       if (M >= (1ull << 31) || p.total_items >= (1ll << 31)) {
