@@ -36,12 +36,16 @@ namespace q8 {
 
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kMmaWarp = kEpiWarps;
-constexpr int kLoadWarp0 = kMmaWarp + 1;
+constexpr int kMmaWarp = kEpiWarps;   // first UMMA-issuing warp (it also owns the TMEM allocation)
+// UMMA-issuing warps, one lane each; warp w issues for the sub-tiles j = w, w + kMmaWarps, ... of every item.  A single
+// issuing thread was the bottleneck of the write-heavy layers: nvcc wraps each tcgen05.mma in a 15-30 instruction
+// elect/broadcast sequence and the thread shares its scheduler with four epilogue warps (see also the depthwise kernel).
+constexpr int kMmaWarps = 3;  // 16 + 3 + 4 + 1 = 24 warps = 768 threads keeps the 80-register budget of the epilogue
+constexpr int kLoadWarp0 = kMmaWarp + kMmaWarps;
 constexpr int kLoadWarps = 4;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kStoreWarp = kLoadWarp0 + kLoadWarps;       // lanes 0/1: bulk-store issue for epilogue pair 0/1
-constexpr int kThreads = (kStoreWarp + 1) * 32;           // 704
+constexpr int kThreads = (kStoreWarp + 1) * 32;           // 768
 constexpr int kEpiPairThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kMaxRawBufs = 4;
@@ -645,10 +649,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int s = 0; s < p.num_stages; s++) {
       // arrivals per stage: the 128 cp.async loaders, or one expect_tx arrival (TMA) plus the loaders when they stream B
       mbar_init(smem_u32(&ctl.full[s]), VEC == kVecTma ? (p.b_resident ? 1 : 1 + kLoadThreads) : kLoadThreads);
-      mbar_init(smem_u32(&ctl.empty[s]), 1);
+      mbar_init(smem_u32(&ctl.empty[s]), kMmaWarps);  // one tcgen05.commit per issuing warp
     }
     for (int s = 0; s < kMaxAccStages; s++) {
-      mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
+      mbar_init(smem_u32(&ctl.tmem_full[s]), kMmaWarps);
       mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiPairThreads);
     }
     mbar_init(smem_u32(&ctl.b_full), kLoadThreads);
@@ -771,9 +775,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
     cp_async_wait_all();
-  } else if (warp == kMmaWarp) {
+  } else if (warp >= kMmaWarp && warp < kMmaWarp + kMmaWarps) {
     // ===================================== UMMA issue =====================================
     if ((tid & 31) == 0) {
+      const int w = warp - kMmaWarp;
       const uint32_t idesc_main = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, p.b_signed != 0);
       const uint32_t idesc_us = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, true);  // u8 x s8
       const uint32_t b_lbo = (uint32_t) p.n_mma * 16;
@@ -811,20 +816,20 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int t = 0; t < p.bias_steps; t++) {
               const uint64_t ad = umma_desc_kmajor_noswizzle(a_const, kChunkBytes, 128);
               const uint64_t bd = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo, b_lbo, 128);
-              for (int j = 0; j < it.mt_eff; j++) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
+              for (int j = w; j < it.mt_eff; j += kMmaWarps) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
             }
           }
           for (int c = 0; c < cs; c += 2) {
             const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
             const uint64_t bd = umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128);
-            for (int j = 0; j < it.mt_eff; j++)
+            for (int j = w; j < it.mt_eff; j += kMmaWarps)
               umma_i8(d_tmem + j * p.n_mma, umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128),
                       bd, idesc_main, acc);
             if (p.has_b2) {
               // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
               const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
               const uint64_t b2 = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo, b_lbo, 128);
-              for (int j = 0; j < it.mt_eff; j++)
+              for (int j = w; j < it.mt_eff; j += kMmaWarps)
                 umma_i8(d_tmem + j * p.n_mma,
                         umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128), b2, idesc_us, 1u);
             }
