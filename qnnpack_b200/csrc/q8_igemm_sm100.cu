@@ -784,6 +784,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t b_lbo = (uint32_t) p.n_mma * 16;
       const uint32_t sub_bytes = (uint32_t) p.skc * kChunkBytes;
       const uint32_t a_const = smem_base + p.smem_aconst_off;
+      // descriptor templates (strides, version); the 16-byte-granular start address is added per use — every operand
+      // lies below 256 KB, so the 14-bit address field cannot carry into its neighbours
+      const uint64_t a_tmpl = umma_desc_kmajor_noswizzle(0, kChunkBytes, 128);
+      const uint64_t b_tmpl = umma_desc_kmajor_noswizzle(0, b_lbo, 128);
       if (p.b_resident) {
         mbar_wait(smem_u32(&ctl.b_full), 0);
         fence_proxy_async_smem();
@@ -814,24 +818,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (p.folded && ks == 0) {
             // accumulator := folded bias  (A = [255 x31, 1] in every row, B = signed base-255 digits)
             for (int t = 0; t < p.bias_steps; t++) {
-              const uint64_t ad = umma_desc_kmajor_noswizzle(a_const, kChunkBytes, 128);
-              const uint64_t bd = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo, b_lbo, 128);
+              const uint64_t ad = a_tmpl + (a_const >> 4);
+              const uint64_t bd = b_tmpl + ((blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo) >> 4);
               for (int j = w; j < it.mt_eff; j += kMmaWarps) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
             }
           }
           for (int c = 0; c < cs; c += 2) {
             const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
-            const uint64_t bd = umma_desc_kmajor_noswizzle(b_base + c * b_lbo, b_lbo, 128);
+            const uint64_t bd = b_tmpl + ((b_base + c * b_lbo) >> 4);
+            const uint64_t ad0 = a_tmpl + ((a_stage + c * kChunkBytes) >> 4);
+            const uint32_t sub16 = sub_bytes >> 4;
             for (int j = w; j < it.mt_eff; j += kMmaWarps)
-              umma_i8(d_tmem + j * p.n_mma, umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128),
-                      bd, idesc_main, acc);
+              umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, bd, idesc_main, acc);
             if (p.has_b2) {
               // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
               const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
-              const uint64_t b2 = umma_desc_kmajor_noswizzle(blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo, b_lbo, 128);
+              const uint64_t b2 = b_tmpl + ((blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo) >> 4);
               for (int j = w; j < it.mt_eff; j += kMmaWarps)
-                umma_i8(d_tmem + j * p.n_mma,
-                        umma_desc_kmajor_noswizzle(a_stage + j * sub_bytes + c * kChunkBytes, kChunkBytes, 128), b2, idesc_us, 1u);
+                umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, b2, idesc_us, 1u);
             }
           }
           umma_commit(smem_u32(&ctl.empty[stage]));

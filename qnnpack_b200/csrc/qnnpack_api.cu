@@ -238,6 +238,9 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
       int stages = smem_max / stage_bytes;
       if (stages > q8::kDwTcMaxStages) stages = q8::kDwTcMaxStages;
       if (stages < 3 && !(cap == 1 && G == 1 && stages >= 2)) continue;
+      // prefer two channel groups per item over wider tiles (both 16-byte halves of every 32-byte sector move together,
+      // and the units of an item occupy all four UMMA-issuing warps): a single group is accepted only at the narrowest tile
+      if (G == 1 && p->cgs > 1 && cap > 1) continue;
       p->G = G, p->mt = mt, p->xt = xt, p->box_px = box_px, p->plane_tx = plane_tx, p->plane_bytes = plane_bytes;
       p->a_bytes = a_bytes, p->cg_bytes = cg_bytes, p->stage_bytes = stage_bytes, p->num_stages = stages;
       break;
@@ -832,7 +835,7 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       // where one channel group per item fits and the CUDA-core streaming kernel is ~8% faster; QNNP_CUDA_DW_UMMA=1
       // forces the tensor-core path for every eligible shape, QNNP_CUDA_DW_NO_UMMA=1 disables it)
       const bool force_tc = getenv("QNNP_CUDA_DW_UMMA") != nullptr;
-      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32;
+      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32 && getenv("QNNP_CUDA_DW_S2_UMMA") == nullptr;
       const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && getenv("QNNP_CUDA_DW_NO_UMMA") == nullptr &&
           (force_tc || !s2_rows) &&
           ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
