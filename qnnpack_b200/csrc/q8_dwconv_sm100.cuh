@@ -70,6 +70,9 @@ struct DwTcParams {
   int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
   int acc_stride, acc_stages;
   int epi_poll_ns;          // back-off of the epilogue warps' accumulator poll (0 = spin)
+  // item schedule: a CTA's next item is `grid` items further; in (cb, xtile, ytile, nblk) digits that is this step
+  int step_cb, step_x, step_y, step_n;
+  uint32_t inv_g, inv_tail; // ceil(2^16 / g) for g = G and for the last channel block's group count
   int rq_mode;
   Q8Requant rq;
 };

@@ -66,17 +66,43 @@ struct DwItem {
 
 // item = ((nblk * yt + ytile) * xt + xtile) * cblocks + cb: the channel blocks of one spatial tile are neighbours in
 // the schedule, so the CTAs that run them touch the same DRAM lines at about the same time.
-__device__ __forceinline__ DwItem decode_item(const DwTcParams& p, uint32_t item) {
-  DwItem it;
+// Every role walks the same item sequence; the position is kept as mixed-radix digits and advanced by the (host-
+// computed) digits of the grid size, so the three divisions happen once per CTA instead of once per item and role.
+struct ItemPos {
+  int cb, xt, yt, nb;
+};
+
+__device__ __forceinline__ ItemPos first_pos(const DwTcParams& p, uint32_t item) {
+  ItemPos q;
   uint32_t r = item / (uint32_t) p.cblocks;
-  it.cb = (int) (item - r * (uint32_t) p.cblocks);
-  uint32_t q = r / (uint32_t) p.xt;
-  const uint32_t xtile = r - q * (uint32_t) p.xt;
-  r = q / (uint32_t) p.yt;
-  const uint32_t ytile = q - r * (uint32_t) p.yt;
-  it.n0 = (int) r * p.nb;
-  it.oy0 = (int) ytile * 16;
-  it.ox0 = (int) xtile * p.mt * 8;
+  q.cb = (int) (item - r * (uint32_t) p.cblocks);
+  uint32_t s = r / (uint32_t) p.xt;
+  q.xt = (int) (r - s * (uint32_t) p.xt);
+  r = s / (uint32_t) p.yt;
+  q.yt = (int) (s - r * (uint32_t) p.yt);
+  q.nb = (int) r;
+  return q;
+}
+
+__device__ __forceinline__ void advance_pos(const DwTcParams& p, ItemPos& q) {
+  q.cb += p.step_cb;
+  int carry = q.cb >= p.cblocks;
+  q.cb -= carry ? p.cblocks : 0;
+  q.xt += p.step_x + carry;
+  carry = q.xt >= p.xt;
+  q.xt -= carry ? p.xt : 0;
+  q.yt += p.step_y + carry;
+  carry = q.yt >= p.yt;
+  q.yt -= carry ? p.yt : 0;
+  q.nb += p.step_n + carry;
+}
+
+__device__ __forceinline__ DwItem make_item(const DwTcParams& p, const ItemPos& q) {
+  DwItem it;
+  it.cb = q.cb;
+  it.n0 = q.nb * p.nb;
+  it.oy0 = q.yt * 16;
+  it.ox0 = q.xt * p.mt * 8;
   const int left = (p.out_w - it.ox0 + 7) >> 3;
   it.mt_eff = left < p.mt ? left : p.mt;
   const int gl = p.cgs - it.cb * p.G;
@@ -171,10 +197,11 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t
       }
       int stage = 0, as = 0;
       uint32_t phase = 0, as_phase = 0;
-      for (uint32_t item = first; item < total; item += step) {
-        const DwItem it = decode_item(p, item);
+      ItemPos pos = first_pos(p, first);
+      for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
+        const DwItem it = make_item(p, pos);
         const int units = it.mt_eff * it.g_eff;
-        const uint32_t inv = (65536u + (uint32_t) it.g_eff - 1) / (uint32_t) it.g_eff;
+        const uint32_t inv = it.g_eff == p.G ? p.inv_g : p.inv_tail;
         // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
         uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
         const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
@@ -239,8 +266,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (uint32_t item = first; item < total; item += step) {
-        const DwItem it = decode_item(p, item);
+      ItemPos pos = first_pos(p, first);
+      for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
+        const DwItem it = make_item(p, pos);
         mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
         const uint32_t bar = smem_u32(&ctl.full[stage]);
         const uint32_t dst0 = smem_base + (uint32_t) stage * p.stage_bytes;
@@ -277,8 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int img = g / p.Q, oyl = g - img * p.Q;
     int as = 0;
     uint32_t as_phase = 0;
-    for (uint32_t item = first; item < total; item += step) {
-      const DwItem it = decode_item(p, item);
+    ItemPos pos = first_pos(p, first);
+    for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
+      const DwItem it = make_item(p, pos);
       const int n = it.n0 + img, oy = it.oy0 + oyl;
       const bool row_ok = img < p.nb && n < p.batch && oy < p.out_h;
       const int iy0 = oy * S - p.pad_top;
@@ -296,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, gi fastest); pixel, border-class
       // and address arithmetic are redone only when j changes
       const int units = it.mt_eff * it.g_eff;
-      const uint32_t inv = (65536u + (uint32_t) it.g_eff - 1) / (uint32_t) it.g_eff;
+      const uint32_t inv = it.g_eff == p.G ? p.inv_g : p.inv_tail;
       if (h >= units) {  // nothing to read (narrow tail item)
         tc_fence_before_sync();
         mbar_arrive(empty_bar);

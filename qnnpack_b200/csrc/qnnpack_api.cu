@@ -849,6 +849,16 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
         if (const char* ev = getenv("QNNP_CUDA_DW_POLL_NS")) tp.epi_poll_ns = atoi(ev);
         const long long grid = tp.total_items < g_lib.num_sms ? tp.total_items : g_lib.num_sms;
+        {  // digits of the grid size in the item schedule's mixed radix (cb fastest), and the unit-split reciprocals
+          long long r = grid;
+          tp.step_cb = (int) (r % tp.cblocks), r /= tp.cblocks;
+          tp.step_x = (int) (r % tp.xt), r /= tp.xt;
+          tp.step_y = (int) (r % tp.yt), r /= tp.yt;
+          tp.step_n = (int) r;
+          const int tail = tp.cgs - (tp.cblocks - 1) * tp.G;
+          tp.inv_g = (65536u + (uint32_t) tp.G - 1) / (uint32_t) tp.G;
+          tp.inv_tail = (65536u + (uint32_t) tail - 1) / (uint32_t) tail;
+        }
         e = q8::launch_q8_dwconv3x3_umma(tp, &dw_tmap, (int) grid, stream);
         if (e == cudaSuccess) g_lib.dw_umma_launches.fetch_add(1);
       } else if (stream_ok) {
