@@ -72,7 +72,7 @@ struct DwTcParams {
   int epi_poll_ns;          // back-off of the epilogue warps' accumulator poll (0 = spin)
   // item schedule: a CTA's next item is `grid` items further; in (cb, xtile, ytile, nblk) digits that is this step
   int step_cb, step_x, step_y, step_n;
-  uint32_t inv_g, inv_tail; // ceil(2^16 / g) for g = G and for the last channel block's group count
+  uint32_t inv_g, inv_tail; // ceil(2^16 / m) for m = mt and for the sub-tile count of the last x tile
   int rq_mode;
   Q8Requant rq;
 };

@@ -110,10 +110,12 @@ __device__ __forceinline__ DwItem make_item(const DwTcParams& p, const ItemPos& 
   return it;
 }
 
-// unit index -> (sub-tile j, channel group gi) with gi fastest; inv = ceil(2^16 / g_eff) (exact for un < 256)
-__device__ __forceinline__ void unit_split(int un, int g_eff, uint32_t inv, int& j, int& gi) {
-  j = (int) (((uint32_t) un * inv) >> 16);
-  gi = un - j * g_eff;
+// unit index -> (sub-tile j, channel group gi) with j fastest; inv = ceil(2^16 / mt_eff) (exact for un < 256).
+// A warp takes the units h, h+4, ...: with 4, 2 or 1 sub-tiles per item those all lie in ONE sub-tile, so the
+// per-sub-tile work of the epilogue (pixel, border class, addresses) is done once per item.
+__device__ __forceinline__ void unit_split(int un, int mt_eff, uint32_t inv, int& j, int& gi) {
+  gi = (int) (((uint32_t) un * inv) >> 16);
+  j = un - gi * mt_eff;
 }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -201,14 +203,14 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t
       for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
         const DwItem it = make_item(p, pos);
         const int units = it.mt_eff * it.g_eff;
-        const uint32_t inv = it.g_eff == p.G ? p.inv_g : p.inv_tail;
+        const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
         // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
         uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
         const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
 #pragma unroll
         for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
           int j, gi;
-          unit_split(w + i * kMmaWarps, it.g_eff, inv, j, gi);
+          unit_split(w + i * kMmaWarps, it.mt_eff, inv, j, gi);
           b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
           a16[i] = b16[i] + (uint32_t) j * 8;
           dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, gi fastest); pixel, border-class
       // and address arithmetic are redone only when j changes
       const int units = it.mt_eff * it.g_eff;
-      const uint32_t inv = it.g_eff == p.G ? p.inv_g : p.inv_tail;
+      const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
       if (h >= units) {  // nothing to read (narrow tail item)
         tc_fence_before_sync();
         mbar_arrive(empty_bar);
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       bool valid = false;
       for (int un = h; un < units; un += 4) {
         int j, gi;
-        unit_split(un, it.g_eff, inv, j, gi);
+        unit_split(un, it.mt_eff, inv, j, gi);
         if (j != j_cur) {
           j_cur = j;
           const int ox = it.ox0 + 8 * j + px;

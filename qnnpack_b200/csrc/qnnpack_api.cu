@@ -855,8 +855,8 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
           tp.step_x = (int) (r % tp.xt), r /= tp.xt;
           tp.step_y = (int) (r % tp.yt), r /= tp.yt;
           tp.step_n = (int) r;
-          const int tail = tp.cgs - (tp.cblocks - 1) * tp.G;
-          tp.inv_g = (65536u + (uint32_t) tp.G - 1) / (uint32_t) tp.G;
+          const int tail = (tp.out_w + 7) / 8 - (tp.xt - 1) * tp.mt;  // sub-tiles of the last x tile
+          tp.inv_g = (65536u + (uint32_t) tp.mt - 1) / (uint32_t) tp.mt;
           tp.inv_tail = (65536u + (uint32_t) tail - 1) / (uint32_t) tail;
         }
         e = q8::launch_q8_dwconv3x3_umma(tp, &dw_tmap, (int) grid, stream);
