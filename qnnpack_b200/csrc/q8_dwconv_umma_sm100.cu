@@ -41,10 +41,10 @@ namespace {
 
 constexpr int kEpiWarps = 16;
 constexpr int kMmaWarp = kEpiWarps;            // first of the UMMA-issuing warps (it also owns the TMEM allocation)
-constexpr int kMmaWarps = 4;                   // one lane each; they split the units of an item (see below)
+constexpr int kMmaWarps = 7;                   // one lane each; they split the units of an item (see below)
 constexpr int kTmaWarp = kMmaWarp + kMmaWarps;
-constexpr int kThreads = (kTmaWarp + 1) * 32;  // 672
-constexpr int kMaxUnitsPerMmaWarp = 4;         // 16 units (mt * G <= 16) over 4 warps
+constexpr int kThreads = (kTmaWarp + 1) * 32;  // 768 (24 warps: keeps the 80-register budget)
+constexpr int kMaxUnitsPerMmaWarp = 3;         // 16 units (mt * G <= 16) over 7 warps
 constexpr int kTmemCols = 512;
 
 struct __align__(8) Ctl {
@@ -291,13 +291,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp >= kMmaWarp && warp < kMmaWarp + kMmaWarps) {
-    // ===================================== UMMA issue (4 warps, one lane each) =====================================
+    // ===================================== UMMA issue (7 warps, one lane each) =====================================
     // This layer needs one small UMMA (N = 16/32) per ~400 outputs, i.e. one every ~40 cycles per SM.  nvcc wraps every
     // tcgen05.mma in an elect/broadcast sequence (~27 instructions), and an issuing warp shares its sub-partition with
-    // four busy epilogue warps, so one thread manages only one UMMA per ~100 cycles (measured).  Four warps — one per
-    // sub-partition — issue concurrently; warp w owns the units w, w+4, ... of every item.  (Eight issuing warps were
-    // measured 3x SLOWER than four.)
-    // (one copy of the loop for all four: per-warp template instances quadruple the code and were measured 2.3x slower,
+    // four busy epilogue warps, so one thread manages only one UMMA per ~100 cycles (measured).  Seven warps issue
+    // concurrently (1 -> 4 warps: 2x faster; 4 -> 7: another 2-5 %); warp w owns the units w, w+7, ... of every item.
+    // (ONE copy of the loop for all of them: per-warp template instances multiply the code and were measured 2.3x slower,
     // presumably instruction-cache misses)
     mma_role<NB>(p, ctl, smem_base, tmem_base, lane, warp - kMmaWarp, first, step, total);
   } else {
