@@ -485,8 +485,18 @@ struct EpiCtx {
 // NB output bytes (NB/4 packed words, NB = 16 or 32) of row m, columns [c0, c0+NB) of the n-tile.
 // bulk: into the dense smem image of the item's output rows (pitch goc, goc % 4 == 0), later written by ONE
 // cp.async.bulk per item — the TMA engine produces full-width global writes, which strided per-thread stores do not.
-template <int NB>
+// FAST: the item is known to be a full bulk item of full 16-column groups -> unconditional 16-byte staging stores
+template <int NB, bool FAST>
 __device__ __forceinline__ void emit(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, const uint32_t* w) {
+  if constexpr (FAST) {
+    const uint32_t s = e.staging + (uint32_t) (j * kTileM + e.row) * p.goc + c0;
+#pragma unroll
+    for (int h = 0; h < NB / 16; h++)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s + 16 * h), "r"(w[4 * h]), "r"(w[4 * h + 1]), "r"(w[4 * h + 2]),
+                   "r"(w[4 * h + 3])
+                   : "memory");
+    return;
+  }
   const int valid = e.n_valid - c0;
   if (valid <= 0) return;
   if (e.bulk) {
@@ -532,7 +542,7 @@ __device__ __forceinline__ void emit(const IgemmParams& p, const Item& it, const
 // W (16 or 32) accumulator columns of one row: TMEM -> registers -> requantise -> pack -> store.
 // FOLDED: the accumulator already contains bias and zero-point correction (extra UMMAs); otherwise
 // ("ones" mode) the folded bias comes from smem and -kzp*rowsum from accumulator column n_tile.
-template <int RQ, int W, bool FOLDED>
+template <int RQ, int W, bool FOLDED, bool FAST>
 __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& it, const EpiCtx& e, int j, int c0, bool first,
                                               bool last) {
   int32_t v[W];
@@ -551,7 +561,7 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
     tc_fence_before_sync();
     mbar_arrive(e.tmem_empty_bar);
   }
-  if (p.dbg_acc != nullptr) {  // bring-up aid; v[] is only indexed with constants, so it stays in registers
+  if (!FAST && p.dbg_acc != nullptr) {  // bring-up aid; v[] is only indexed with constants, so it stays in registers
     int32_t* d = p.dbg_acc + (((size_t) e.item * p.mt + j) * kTileM + e.row) * p.n_mma;
 #pragma unroll
     for (int i = 0; i < W; i++) d[c0 + i] = v[i];
@@ -589,12 +599,12 @@ __device__ __forceinline__ void epilogue_cols(const IgemmParams& p, const Item& 
     for (int t = 0; t < W / 4; t++) w[t] = requant_pack4_generic(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3], p.rq);
   }
   if (first && p.out_mode == 1) mbar_wait(e.out_free_bar, e.out_free_parity);  // the previous bulk store has left staging
-  emit<W>(p, it, e, j, c0, w);
+  emit<W, FAST>(p, it, e, j, c0, w);
 }
 
 // One epilogue warp = lane quarter q (warp % 4) of its pair's accumulator stage; the two warps of a pair that share
 // a quarter take alternate (sub-tile, column-block) units of the item.
-template <int RQ, bool FOLDED>
+template <int RQ, bool FOLDED, bool FAST>
 __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
   constexpr int W = FOLDED ? 32 : 16;
   const int full = p.n_tile / W;            // full-width units per sub-tile
@@ -608,9 +618,9 @@ __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& 
   for (int u = half; u < units; u += 2) {
     const bool first = u == half, last = u + 2 >= units;
     if (c < full) {
-      epilogue_cols<RQ, W, FOLDED>(p, it, e, j, c * W, first, last);
+      epilogue_cols<RQ, W, FOLDED, FAST>(p, it, e, j, c * W, first, last);
     } else {
-      epilogue_cols<RQ, 16, FOLDED>(p, it, e, j, c * W, first, last);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
+      epilogue_cols<RQ, 16, FOLDED, FAST>(p, it, e, j, c * W, first, last);  // 16-column remainder (FOLDED, n_tile % 32 == 16)
     }
     c += 2;
     while (c >= per_sub) {
@@ -622,10 +632,20 @@ __device__ __forceinline__ void epilogue_item(const IgemmParams& p, const Item& 
 
 template <int RQ>
 __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const Item& it, const EpiCtx& e, int half) {
+  // fast variant (specialised requantisation forms only): full bulk item, every 16-column group complete, no debug dump
+  const bool fast = (RQ == 5 || RQ == 6) && e.bulk && p.dbg_acc == nullptr && (p.goc & 15) == 0 && e.n_valid == p.n_tile;
   if (p.folded) {
-    epilogue_item<RQ, true>(p, it, e, half);
+    if (fast) {
+      epilogue_item<RQ, true, (RQ == 5 || RQ == 6)>(p, it, e, half);
+    } else {
+      epilogue_item<RQ, true, false>(p, it, e, half);
+    }
   } else {
-    epilogue_item<RQ, false>(p, it, e, half);
+    if (fast) {
+      epilogue_item<RQ, false, (RQ == 5 || RQ == 6)>(p, it, e, half);
+    } else {
+      epilogue_item<RQ, false, false>(p, it, e, half);
+    }
   }
 }
 
