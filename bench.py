@@ -172,9 +172,9 @@ def b200_main(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one line (the JSON): keep NCCL's version banner off it unless asked otherwise
-        if "QNNP_BENCH_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one line (the JSON): NCCL writes its version banner / debug lines to stdout by
+        # default, so send them to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import qnnpack_b200
