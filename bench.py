@@ -167,13 +167,17 @@ def b200_main(args, rank, local_rank, world):
     import torch.distributed as dist
 
     faulthandler.dump_traceback_later(240, exit=False)  # a hung collective or kernel leaves a stack trace on stderr
+    # stdout must carry exactly one line, the JSON.  Native libraries write to file descriptor 1 behind Python's back
+    # (NCCL prints its version banner there), so fd 1 is pointed at stderr for the duration of the run and the result
+    # goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     os.environ["QNNP_CUDA_DEVICE"] = str(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one line (the JSON): NCCL writes its version banner / debug lines to stdout by
-        # default, so send them to stderr instead
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -363,7 +367,7 @@ def b200_main(args, rank, local_rank, world):
         "stack_ops_g": stack.total_ops(B) / 1e9, "stack_algorithmic_gb": stack.total_bytes(B) / 1e9,
         "stack_frac_of_hbm_roofline": (stack.total_bytes(B) / 1e6 / peak_gbs) / ms_per_step,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=result_out, flush=True)
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
