@@ -6,23 +6,27 @@
 //   src/indirection.c:18-79 (the pointer table is never built: tap -> address is computed in the load stage)
 //   the Q31 epilogue those micro-kernels inline (src/q8gemm/4x4c2-sse2.c:178-278)
 //
-// Arithmetic (bit-exact by construction, all int32, order independent):
-//   acc[m][n] = bias'[n] + sum_k a[m][k] * w[n][k] - kzp * sum_k a[m][k]
-// with bias' = b + K*izp*kzp - izp*sum_k w (the reference's packed bias) and padded taps reading the
-// byte izp, i.e. the reference's own "XZP" algebra (src/q8gemm/4x8c2-xzp-neon.c:26-67, pack.h:216-232)
-// which lets the tensor core run raw u8 x u8 -> s32.  sum_k a[m][k] falls out of the same UMMA as one
-// extra B row of ones (accumulator column n_tile).
+// Arithmetic (bit-exact by construction, all int32, order independent).  Two regroupings of the
+// reference's  acc = bias' + sum_k a_k (w_k - kzp),  bias' = b + K*izp*kzp - izp*sum_k w,  padded taps reading izp:
+//   "folded": every additive term runs on the tensor core — u8 x s8 UMMAs with B1 = w XOR 0x80, a constant
+//             (128 - kzp) operand, and bias' as base-255 digits against a constant A row; the epilogue only requantises;
+//   "ones"  : the reference's own XZP algebra (src/q8gemm/4x8c2-xzp-neon.c:26-67, pack.h:216-232): raw u8 x u8 UMMA,
+//             sum_k a[m][k] from one extra B row of ones, epilogue adds bias'[n] - kzp * rowsum[m].
 //
-// Structure (one CTA per SM, 672 threads):
-//   warps 0-15  epilogue: TMEM -> regs -> Q31 requant -> uint8 -> 32-byte global stores; every warp works on every
-//               work item (lane quarter = warp % 4; the 4 warps of a quarter interleave column blocks)
-//   warp  16    TMEM allocation + UMMA issue (one lane)
-//   warps 17-20 loaders: cp.async global -> smem, canonical K-major no-swizzle layout [sub-tile][k-chunk][row][16 B]
+// Structure (one CTA per SM, 768 threads):
+//   warps 0-15   epilogue, two pairs of 8 warps alternating work items: tcgen05.ld -> Q31 requantisation ("U" form,
+//                requant_math.h) -> saturating pack -> the pair's smem image of the output tile (or direct stores)
+//   warps 16-18  TMEM allocation (warp 16) + UMMA issue, one lane each, sub-tiles split round-robin
+//   warps 19-22  loaders: TMA (1x1 / FC), cp.async (general conv: tap -> address in the load stage), or the raw-row
+//                ring + branch-free K-row builder (3x3 over 3 channels); canonical K-major no-swizzle layout
+//                [sub-tile][k-chunk][row][16 B]
+//   warp  23     lanes 0/1: one bulk (1-D TMA) store per finished item of pair 0/1
 // A work item is `mt` (<= 8) consecutive 128-row sub-tiles x one n-tile: the sub-tiles' accumulators sit side
 // by side in one TMEM stage (mt * n_mma <= 256 columns), which amortises every per-item synchronisation
 // over up to 1024 rows — essential for the narrow (N = 16..96) projection layers.
-// Pipelines: smem ring full/empty mbarriers (loaders <-> UMMA), two TMEM accumulator stages
-// full/empty (UMMA <-> epilogue pairs).  int32 accumulators never leave TMEM/registers.
+// Pipelines: smem ring full/empty mbarriers (loaders <-> UMMA), 2-4 TMEM accumulator stages full/empty
+// (UMMA <-> epilogue pairs), out_full/out_free (epilogue pair <-> store lane).  int32 accumulators never leave
+// TMEM/registers.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,7 +39,6 @@
 namespace q8 {
 
 constexpr int kEpiWarps = 16;
-constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = kEpiWarps;   // first UMMA-issuing warp (it also owns the TMEM allocation)
 // UMMA-issuing warps, one lane each; warp w issues for the sub-tiles j = w, w + kMmaWarps, ... of every item.  A single
 // issuing thread was the bottleneck of the write-heavy layers: nvcc wraps each tcgen05.mma in a 15-30 instruction
@@ -257,13 +260,9 @@ __device__ __forceinline__ void run9_load_smem(uint32_t saddr, uint32_t (&w)[3])
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[2]) : "r"(base + 8));
 }
 
-// RAW: the 9-byte runs come from the raw-row staging buffer at shared address `raw` (see raw_segments) instead of global
-// raw_n0 / raw_b0 / raw_b1: image of the first staged range and, for both ranges, the shared address of the (virtual)
-// byte (row 0, column 0) of their image — so a run's address is one multiply-add away
-template <bool RAW>
-__device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid, int raw_n0,
-                                                 uint32_t raw_b0, uint32_t raw_b1) {
-  constexpr int NB = RAW ? 2 : 4;  // pixels (sub-tiles) in flight per thread (shared-memory reads need less cover)
+// Global-memory variant (used when the tensor cannot be bulk-copied: unaligned base / size, or tiny images)
+__device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Item& it, uint32_t a_stage, int ltid) {
+  constexpr int NB = 4;  // pixels (sub-tiles) in flight per thread
   const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
   // pixel of this thread in sub-tile 0 by division (M < 2^31, host-checked); the following sub-tiles are 128 pixels
   // further along the same NHW order, reached by stepping — two divisions per item instead of two per pixel
@@ -302,13 +301,7 @@ __device__ __forceinline__ void load_a_conv_run9(const IgemmParams& p, const Ite
         const uint8_t* src = img + (size_t) (rowok ? iy : 0) * p.in_w * 3;
         info[jj] |= (((uint32_t) reinterpret_cast<uintptr_t>(src) & 3u) | (st << 2)) << (4 * ky);
         if (st == 0) {
-          if constexpr (RAW) {
-            // same bytes, staged: shared address = buffer + copy offset + (row, column) inside the copied rows; the
-            // copy starts 16-byte aligned in both spaces, so the low address bits (the funnel-shift amount) agree
-            run9_load_smem(((int) n == raw_n0 ? raw_b0 : raw_b1) + (uint32_t) (iy * p.in_w + ix0) * 3u, w[jj][ky]);
-          } else {
-            run9_load(src, w[jj][ky]);
-          }
+          run9_load(src, w[jj][ky]);
         } else {
           w[jj][ky][0] = w[jj][ky][1] = w[jj][ky][2] = fill;
         }
@@ -760,7 +753,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else if constexpr (MODE == kModeGemm) {
           load_a_gemm<VEC>(p, it, ks, a_stage, ltid);
         } else if constexpr (VEC == 0) {
-          load_a_conv_run9<false>(p, it, a_stage, ltid, 0, 0u, 0u);  // K = 27 fits one stage
+          load_a_conv_run9(p, it, a_stage, ltid);  // K = 27 fits one stage
         } else if constexpr (VEC == kVecRaw9) {
           if (ltid == 0 && pitem < p.total_items) issue_raw();  // keep the ring of row requests full
           RawSeg sg[2];

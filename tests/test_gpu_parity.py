@@ -83,6 +83,9 @@ STEM_CASES = [
     CS.conv_case("stem_70x74_b4", 4, 70, 74, 1, 3, 24, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
     CS.conv_case("stem_s1_40_b4", 4, 40, 40, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
     CS.conv_case("stem_nopad_66_b4", 4, 66, 66, 1, 3, 32, ks=(3, 3), stride=(2, 2)),
+    # images too small for the raw-row ring (an item would span more than two): per-thread global gather instead
+    CS.conv_case("stem_small_20_b3", 3, 20, 20, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
+    CS.conv_case("stem_small_s1_9x11_b5", 5, 9, 11, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
 ]
 
 
