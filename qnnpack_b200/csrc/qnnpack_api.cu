@@ -185,8 +185,10 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   const int Qw = (rows_needed + s - 1) / s;
   p->whole = Qw <= 16 ? 1 : 0;
   if (p->whole) {
+    // stack as many images as still have ALL their valid rows inside the UMMA's 16 row groups: image i occupies
+    // groups [i*Q, i*Q + OH), the Q - OH groups after them are its bottom halo and produce nothing
     p->Q = Qw;
-    p->nb = (16 + Qw - 1) / Qw;
+    p->nb = 1 + (16 - OH) / Qw;
     p->box_rows = s * Qw;
     p->yt = 1;
   } else {

@@ -120,6 +120,8 @@ CASES = [
     (32, 2, 9, 12, 1, (0, 0)),           # no padding
     (16, 1, 18, 16, 2, (0, 0)),          # stride 2 without padding: planes swap roles
     (16, 2, 5, 70, 1, (1, 1)),           # wide rows: several x tiles
+    (16, 3, 28, 28, 2, (1, 1)),          # 28 -> 14 rows, stride 2: Q = 15, a second stacked image would lose rows
+    (16, 3, 18, 6, 2, (0, 0)),           # Q = 9, 8 valid rows: likewise
 ]
 
 
@@ -129,7 +131,7 @@ def test_plan_addressing_reproduces_the_convolution(plan, c, n, h, w, s, pad):
     assert d is not None
     assert d["smem_total"] <= SMEM_OPTIN - 1024 and d["num_stages"] >= 2
     assert d["acc_stride"] <= 256 and d["mt"] * d["G"] * d["nb_cols"] == d["acc_stride"]
-    assert d["nb"] * d["Q"] >= 16 if d["whole"] else d["Q"] == 16
+    assert (d["nb"] - 1) * d["Q"] + oh <= 16 if d["whole"] else d["Q"] == 16   # every valid row inside the 16 groups
     for u in range(5):  # descriptor fields are 14 bits of 16-byte units
         assert d["a_off%d" % u] % 16 == 0 and d["a_lbo%d" % u] % 16 == 0 and 0 <= d["a_lbo%d" % u] < (1 << 18)
     assert d["sbo"] % 16 == 0 and d["sbo"] < (1 << 18)
@@ -141,6 +143,38 @@ def test_plan_addressing_reproduces_the_convolution(plan, c, n, h, w, s, pad):
     got = replay(d, x, wk, bias, izp, kzp, s, pad, oh, ow)
     want = direct(x, wk, bias, izp, kzp, s, pad, oh, ow)
     assert np.array_equal(got, want)
+
+
+def _random_geometries(count, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        s = int(rng.integers(1, 3))
+        c = int(rng.choice([16, 32, 48, 80]))
+        n = int(rng.integers(1, 4))
+        h = int(rng.integers(3, 26))
+        w = int(rng.integers(3, 30))
+        if s == 2 and w % 2:
+            w += 1
+        pad = (int(rng.integers(0, 3)), int(rng.integers(0, 3)))
+        if (h + 2 * pad[0] - 3) // s + 1 < 1 or (w + 2 * pad[1] - 3) // s + 1 < 1:
+            continue
+        out.append((c, n, h, w, s, pad))
+    return out
+
+
+@pytest.mark.parametrize("c,n,h,w,s,pad", _random_geometries(24, 2026))
+def test_plan_addressing_on_random_geometries(plan, c, n, h, w, s, pad):
+    """Same replay on random shapes: odd sizes, paddings 0..2 on either axis, both strides, 1-3 images."""
+    d, oh, ow = plan(c, n, h, w, s, pad)
+    assert d is not None, (c, n, h, w, s, pad)
+    assert d["smem_total"] <= SMEM_OPTIN - 1024 and d["acc_stride"] <= 256 and d["mt"] * d["G"] <= 16
+    rng = np.random.default_rng(h * 131 + w * 7 + s)
+    x = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+    wk = rng.integers(0, 256, (c, 9), dtype=np.uint8)
+    bias = rng.integers(-100000, 100000, c).astype(np.int64)
+    izp, kzp = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+    assert np.array_equal(replay(d, x, wk, bias, izp, kzp, s, pad, oh, ow), direct(x, wk, bias, izp, kzp, s, pad, oh, ow))
 
 
 def test_mobilenet_depthwise_layers_are_eligible_and_fit(plan):

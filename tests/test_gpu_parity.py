@@ -63,6 +63,10 @@ DW_TC_CASES = [
     CS.conv_case("tc_c160_112", 1, 112, 112, 160, 1, 1, **DW_TC),
     CS.conv_case("tc_c32_out_stride", 1, 10, 10, 32, 1, 1, out_extra=16, **DW_TC),
     CS.conv_case("tc_c32_in_stride", 1, 10, 10, 32, 1, 1, in_extra=16, **DW_TC),
+    # whole-image mode where a second stacked image would not fit its rows into the 16 row groups (found by the CPU replay)
+    CS.conv_case("tc_c32_s2_28_b3", 3, 28, 28, 32, 1, 1, stride=(2, 2), **DW_TC),
+    CS.conv_case("tc_c16_s2_18x6_nopad_b3", 3, 18, 6, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
+    CS.conv_case("tc_c32_12x12_b5", 5, 12, 12, 32, 1, 1, **DW_TC),
 ]
 
 
