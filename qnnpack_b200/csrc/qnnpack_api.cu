@@ -270,6 +270,18 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   return true;
 }
 
+// CTAs of a persistent kernel: one per SM, never more than there are work items.  QNNP_CUDA_MAX_CTAS=n shrinks the grid
+// so that small test shapes still give every CTA many consecutive items (ring wrap-around, accumulator-stage parity,
+// item stepping) — the parity tests run selected cases that way.
+long long persistent_grid(long long total_items) {
+  long long grid = total_items < g_lib.num_sms ? total_items : g_lib.num_sms;
+  if (const char* e = getenv("QNNP_CUDA_MAX_CTAS")) {
+    const long long v = atoll(e);
+    if (v >= 1 && v < grid) grid = v;
+  }
+  return grid;
+}
+
 bool is_device_pointer(const void* ptr) {
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
@@ -807,7 +819,7 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         vec = 32;
         tmap_ptr = &tmap;
       }
-      long long grid = p.total_items < g_lib.num_sms ? p.total_items : g_lib.num_sms;
+      const long long grid = persistent_grid(p.total_items);
       e = q8::launch_q8_igemm(p, mode, vec, tmap_ptr, (int) grid, stream);
       break;
     }
@@ -850,7 +862,7 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         tp.out_stride = (long long) op->out_stride;
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
         if (const char* ev = getenv("QNNP_CUDA_DW_POLL_NS")) tp.epi_poll_ns = atoi(ev);
-        const long long grid = tp.total_items < g_lib.num_sms ? tp.total_items : g_lib.num_sms;
+        const long long grid = persistent_grid(tp.total_items);
         {  // digits of the grid size in the item schedule's mixed radix (cb fastest), and the unit-split reciprocals
           long long r = grid;
           tp.step_cb = (int) (r % tp.cblocks), r /= tp.cblocks;

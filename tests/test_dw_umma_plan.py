@@ -190,3 +190,42 @@ def test_mobilenet_depthwise_layers_are_eligible_and_fit(plan):
 def test_ineligible_shapes_fall_back(plan):
     assert plan(24, 1, 8, 8, 1)[0] is None      # channels not a multiple of 16
     assert plan(16, 1, 9, 9, 2)[0] is None      # stride 2 needs an even width
+
+
+def test_item_stepping_is_equivalent_to_decoding():
+    """Model of the kernel's item walk (q8_dwconv_umma_sm100.cu: first_pos / advance_pos with the host's step digits):
+    a CTA's k-th item, reached by adding the grid size in (cb, xtile, ytile, nblk) digits with carries, must be the item
+    the flat index first + k * grid decodes to."""
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        cblocks, xt, yt, nt = (int(v) for v in rng.integers(1, 9, 4))
+        nt = int(rng.integers(1, 200))
+        total = cblocks * xt * yt * nt
+        grid = int(rng.integers(1, min(total, 148) + 1))
+        r = grid
+        step_cb, r = r % cblocks, r // cblocks
+        step_x, r = r % xt, r // xt
+        step_y, r = r % yt, r // yt
+        step_n = r
+        for first in {0, grid - 1, int(rng.integers(0, grid))}:
+            q, r = divmod(first, cblocks)
+            cb = r
+            q, x = divmod(q, xt)
+            nb, y = divmod(q, yt)
+            item = first
+            while item < total:
+                want_q, want_cb = divmod(item, cblocks)
+                want_q, want_x = divmod(want_q, xt)
+                want_nb, want_y = divmod(want_q, yt)
+                assert (cb, x, y, nb) == (want_cb, want_x, want_y, want_nb)
+                cb += step_cb
+                carry = cb >= cblocks
+                cb -= cblocks if carry else 0
+                x += step_x + carry
+                carry = x >= xt
+                x -= xt if carry else 0
+                y += step_y + carry
+                carry = y >= yt
+                y -= yt if carry else 0
+                nb += step_n + carry
+                item += grid

@@ -180,3 +180,31 @@ def test_mobilenet_v2_layer_batch1(gpu_lib, golden, entry):
     x, k, b, kw = U.conv_setup(case)
     y = U.run_conv(gpu_lib, case, x, k, b, kw)
     assert U.digest(y) == str(golden[f"mnv2/{case['name']}/y_digest"]), case["name"]
+
+
+# ---- persistent loops: many consecutive work items per CTA ----------------------------------------------------
+# With 148 CTAs the shapes above give every CTA at most one or two items.  QNNP_CUDA_MAX_CTAS shrinks the grid so that
+# each CTA walks a long item sequence: smem-ring wrap-around, TMEM accumulator-stage parity, staged bulk stores,
+# raw-row ring, mixed-radix item stepping of the depthwise kernel — all compared byte for byte with the oracle.
+PERSISTENT_CASES = [
+    CS.conv_case("pers_1x1_expand", 2, 40, 40, 1, 16, 96),                      # folded, TMA, bulk stores, mt = 2
+    CS.conv_case("pers_1x1_project", 2, 40, 40, 1, 96, 24),                     # ones mode, several k-chunks
+    CS.conv_case("pers_1x1_n144", 1, 36, 36, 1, 24, 144),                       # 16-column remainder units
+    CS.conv_case("pers_1x1_wide", 1, 14, 14, 1, 320, 1280),                     # streamed weights, 5 n-tiles
+    CS.conv_case("pers_3x3_conv", 1, 30, 30, 1, 16, 32, ks=(3, 3), pad=(1, 1, 1, 1)),   # cp.async conv loader
+    CS.conv_case("pers_stem", 3, 72, 72, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),  # raw-row ring
+    CS.conv_case("pers_dw_s1", 5, 40, 40, 64, 1, 1, **DW_TC),                   # tcgen05 depthwise, row tiles
+    CS.conv_case("pers_dw_s2", 5, 40, 40, 64, 1, 1, stride=(2, 2), **DW_TC),
+    CS.conv_case("pers_dw_stacked", 9, 7, 7, 96, 1, 1, **DW_TC),                # stacked images, odd batch
+    CS.conv_case("pers_dw_c20", 3, 30, 30, 20, 1, 1, **DW_TC),                  # streaming dp4a kernel
+]
+
+
+@pytest.mark.timeout(120, method="thread")   # a wedged kernel must fail the test, not hang the box
+@pytest.mark.parametrize("ctas", [1, 3])
+@pytest.mark.parametrize("case", PERSISTENT_CASES, ids=lambda c: c["name"])
+def test_many_items_per_cta(gpu_lib, oracle_c, case, ctas, monkeypatch):
+    monkeypatch.setenv("QNNP_CUDA_MAX_CTAS", str(ctas))
+    monkeypatch.setenv("QNNP_CUDA_DW_UMMA", "1")
+    x, k, b, kw = U.conv_setup(case)
+    U.assert_same_bytes(U.run_conv(gpu_lib, case, x, k, b, kw), U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
