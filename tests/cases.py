@@ -206,3 +206,55 @@ def derive_output_quant(acc):
     oscale = float(np.float32(max((amax - amin) / 255.0, 1.0 + 2.0 ** -20)))
     ozp = int(np.clip(round(127.5 - (amax + amin) / 2.0 / oscale), 0, 255))
     return oscale, ozp
+
+
+# ---- round-1 additions: shapes that select specific device paths.  The GPU tests compare these with the oracle; the CPU
+# suite pins the oracle to the compiled reference on the same cases (tests/test_oracle.py). -------------------------------
+# depthwise shapes that take the tcgen05 path (channels % 16 == 0, dense pixels): geometry classes of its planner —
+# 16-row tiles vs whole images stacked, one vs two parity planes, ragged tiles, every weight-operand mode, clamps
+DW_TC = dict(ks=(3, 3), pad=(1, 1, 1, 1))
+DW_TC_CASES = [
+    conv_case("tc_c16_rows", 1, 20, 23, 16, 1, 1, **DW_TC),
+    conv_case("tc_c48_7x7_stack2", 3, 7, 7, 48, 1, 1, **DW_TC),
+    conv_case("tc_c32_14x14", 3, 14, 14, 32, 1, 1, **DW_TC),
+    conv_case("tc_c32_s2_rows", 1, 40, 36, 32, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c16_s2_whole", 3, 14, 14, 16, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c32_nopad", 2, 9, 12, 32, 1, 1, ks=(3, 3)),
+    conv_case("tc_c16_s2_nopad", 1, 18, 16, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
+    conv_case("tc_c16_wide", 2, 5, 70, 16, 1, 1, **DW_TC),
+    conv_case("tc_c64_kzp128_s8", 2, 17, 17, 64, 1, 1, kzp=128, **DW_TC),      # w - kzp fits s8: one operand
+    conv_case("tc_c64_kzp0_u8", 2, 17, 17, 64, 1, 1, kzp=0, izp=3, **DW_TC),    # u8 weights
+    conv_case("tc_c32_kzp255", 1, 12, 12, 32, 1, 1, kzp=255, izp=255, **DW_TC),
+    conv_case("tc_c32_clamp", 1, 12, 12, 32, 1, 1, qmin=40, qmax=200, **DW_TC),
+    conv_case("tc_c160_112", 1, 112, 112, 160, 1, 1, **DW_TC),
+    conv_case("tc_c32_out_stride", 1, 10, 10, 32, 1, 1, out_extra=16, **DW_TC),
+    conv_case("tc_c32_in_stride", 1, 10, 10, 32, 1, 1, in_extra=16, **DW_TC),
+    # whole-image mode where a second stacked image would not fit its rows into the 16 row groups (found by the CPU replay)
+    conv_case("tc_c32_s2_28_b3", 3, 28, 28, 32, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c16_s2_18x6_nopad_b3", 3, 18, 6, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
+    conv_case("tc_c32_12x12_b5", 5, 12, 12, 32, 1, 1, **DW_TC),
+]
+
+STEM_CASES = [
+    conv_case("stem_72_b5", 5, 72, 72, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
+    conv_case("stem_70x74_b4", 4, 70, 74, 1, 3, 24, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
+    conv_case("stem_s1_40_b4", 4, 40, 40, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
+    conv_case("stem_nopad_66_b4", 4, 66, 66, 1, 3, 32, ks=(3, 3), stride=(2, 2)),
+    # images too small for the raw-row ring (an item would span more than two): per-thread global gather instead
+    conv_case("stem_small_20_b3", 3, 20, 20, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
+    conv_case("stem_small_s1_9x11_b5", 5, 9, 11, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
+]
+
+PERSISTENT_CASES = [
+    conv_case("pers_1x1_expand", 2, 40, 40, 1, 16, 96),                      # folded, TMA, bulk stores, mt = 2
+    conv_case("pers_1x1_project", 2, 40, 40, 1, 96, 24),                     # ones mode, several k-chunks
+    conv_case("pers_1x1_n144", 1, 36, 36, 1, 24, 144),                       # 16-column remainder units
+    conv_case("pers_1x1_wide", 1, 14, 14, 1, 320, 1280),                     # streamed weights, 5 n-tiles
+    conv_case("pers_3x3_conv", 1, 30, 30, 1, 16, 32, ks=(3, 3), pad=(1, 1, 1, 1)),   # cp.async conv loader
+    conv_case("pers_stem", 3, 72, 72, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),  # raw-row ring
+    conv_case("pers_dw_s1", 5, 40, 40, 64, 1, 1, **DW_TC),                   # tcgen05 depthwise, row tiles
+    conv_case("pers_dw_s2", 5, 40, 40, 64, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("pers_dw_stacked", 9, 7, 7, 96, 1, 1, **DW_TC),                # stacked images, odd batch
+    conv_case("pers_dw_c20", 3, 30, 30, 20, 1, 1, **DW_TC),                  # streaming dp4a kernel
+]
+

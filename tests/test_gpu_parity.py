@@ -46,31 +46,9 @@ def test_q8dwconv(gpu_lib, golden, case):
 
 # depthwise shapes that take the tcgen05 path (channels % 16 == 0, dense pixels): geometry classes of its planner —
 # 16-row tiles vs whole images stacked, one vs two parity planes, ragged tiles, every weight-operand mode, clamps
-DW_TC = dict(ks=(3, 3), pad=(1, 1, 1, 1))
-DW_TC_CASES = [
-    CS.conv_case("tc_c16_rows", 1, 20, 23, 16, 1, 1, **DW_TC),
-    CS.conv_case("tc_c48_7x7_stack2", 3, 7, 7, 48, 1, 1, **DW_TC),
-    CS.conv_case("tc_c32_14x14", 3, 14, 14, 32, 1, 1, **DW_TC),
-    CS.conv_case("tc_c32_s2_rows", 1, 40, 36, 32, 1, 1, stride=(2, 2), **DW_TC),
-    CS.conv_case("tc_c16_s2_whole", 3, 14, 14, 16, 1, 1, stride=(2, 2), **DW_TC),
-    CS.conv_case("tc_c32_nopad", 2, 9, 12, 32, 1, 1, ks=(3, 3)),
-    CS.conv_case("tc_c16_s2_nopad", 1, 18, 16, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
-    CS.conv_case("tc_c16_wide", 2, 5, 70, 16, 1, 1, **DW_TC),
-    CS.conv_case("tc_c64_kzp128_s8", 2, 17, 17, 64, 1, 1, kzp=128, **DW_TC),      # w - kzp fits s8: one operand
-    CS.conv_case("tc_c64_kzp0_u8", 2, 17, 17, 64, 1, 1, kzp=0, izp=3, **DW_TC),    # u8 weights
-    CS.conv_case("tc_c32_kzp255", 1, 12, 12, 32, 1, 1, kzp=255, izp=255, **DW_TC),
-    CS.conv_case("tc_c32_clamp", 1, 12, 12, 32, 1, 1, qmin=40, qmax=200, **DW_TC),
-    CS.conv_case("tc_c160_112", 1, 112, 112, 160, 1, 1, **DW_TC),
-    CS.conv_case("tc_c32_out_stride", 1, 10, 10, 32, 1, 1, out_extra=16, **DW_TC),
-    CS.conv_case("tc_c32_in_stride", 1, 10, 10, 32, 1, 1, in_extra=16, **DW_TC),
-    # whole-image mode where a second stacked image would not fit its rows into the 16 row groups (found by the CPU replay)
-    CS.conv_case("tc_c32_s2_28_b3", 3, 28, 28, 32, 1, 1, stride=(2, 2), **DW_TC),
-    CS.conv_case("tc_c16_s2_18x6_nopad_b3", 3, 18, 6, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
-    CS.conv_case("tc_c32_12x12_b5", 5, 12, 12, 32, 1, 1, **DW_TC),
-]
 
 
-@pytest.mark.parametrize("case", DW_TC_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", CS.DW_TC_CASES, ids=lambda c: c["name"])
 def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case, monkeypatch):
     monkeypatch.setenv("QNNP_CUDA_DW_UMMA", "1")   # also where the router would prefer the CUDA-core kernel
     x, k, b, kw = U.conv_setup(case)
@@ -82,18 +60,9 @@ def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case, monkeypatch):
 
 # 3x3 over 3 dense channels (the MobileNetV2 stem shape class): run loader fed from bulk-staged raw rows; the items
 # of these cases straddle image boundaries and rows that are not multiples of 16 bytes
-STEM_CASES = [
-    CS.conv_case("stem_72_b5", 5, 72, 72, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
-    CS.conv_case("stem_70x74_b4", 4, 70, 74, 1, 3, 24, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
-    CS.conv_case("stem_s1_40_b4", 4, 40, 40, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
-    CS.conv_case("stem_nopad_66_b4", 4, 66, 66, 1, 3, 32, ks=(3, 3), stride=(2, 2)),
-    # images too small for the raw-row ring (an item would span more than two): per-thread global gather instead
-    CS.conv_case("stem_small_20_b3", 3, 20, 20, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),
-    CS.conv_case("stem_small_s1_9x11_b5", 5, 9, 11, 1, 3, 16, ks=(3, 3), pad=(1, 1, 1, 1)),
-]
 
 
-@pytest.mark.parametrize("case", STEM_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", CS.STEM_CASES, ids=lambda c: c["name"])
 def test_stem_conv_raw_row_loader(gpu_lib, oracle_c, case):
     x, k, b, kw = U.conv_setup(case)
     U.assert_same_bytes(U.run_conv(gpu_lib, case, x, k, b, kw), U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
@@ -186,23 +155,11 @@ def test_mobilenet_v2_layer_batch1(gpu_lib, golden, entry):
 # With 148 CTAs the shapes above give every CTA at most one or two items.  QNNP_CUDA_MAX_CTAS shrinks the grid so that
 # each CTA walks a long item sequence: smem-ring wrap-around, TMEM accumulator-stage parity, staged bulk stores,
 # raw-row ring, mixed-radix item stepping of the depthwise kernel — all compared byte for byte with the oracle.
-PERSISTENT_CASES = [
-    CS.conv_case("pers_1x1_expand", 2, 40, 40, 1, 16, 96),                      # folded, TMA, bulk stores, mt = 2
-    CS.conv_case("pers_1x1_project", 2, 40, 40, 1, 96, 24),                     # ones mode, several k-chunks
-    CS.conv_case("pers_1x1_n144", 1, 36, 36, 1, 24, 144),                       # 16-column remainder units
-    CS.conv_case("pers_1x1_wide", 1, 14, 14, 1, 320, 1280),                     # streamed weights, 5 n-tiles
-    CS.conv_case("pers_3x3_conv", 1, 30, 30, 1, 16, 32, ks=(3, 3), pad=(1, 1, 1, 1)),   # cp.async conv loader
-    CS.conv_case("pers_stem", 3, 72, 72, 1, 3, 32, ks=(3, 3), stride=(2, 2), pad=(1, 1, 1, 1)),  # raw-row ring
-    CS.conv_case("pers_dw_s1", 5, 40, 40, 64, 1, 1, **DW_TC),                   # tcgen05 depthwise, row tiles
-    CS.conv_case("pers_dw_s2", 5, 40, 40, 64, 1, 1, stride=(2, 2), **DW_TC),
-    CS.conv_case("pers_dw_stacked", 9, 7, 7, 96, 1, 1, **DW_TC),                # stacked images, odd batch
-    CS.conv_case("pers_dw_c20", 3, 30, 30, 20, 1, 1, **DW_TC),                  # streaming dp4a kernel
-]
 
 
 @pytest.mark.timeout(120, method="thread")   # a wedged kernel must fail the test, not hang the box
 @pytest.mark.parametrize("ctas", [1, 3])
-@pytest.mark.parametrize("case", PERSISTENT_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", CS.PERSISTENT_CASES, ids=lambda c: c["name"])
 def test_many_items_per_cta(gpu_lib, oracle_c, case, ctas, monkeypatch):
     monkeypatch.setenv("QNNP_CUDA_MAX_CTAS", str(ctas))
     monkeypatch.setenv("QNNP_CUDA_DW_UMMA", "1")

@@ -122,6 +122,14 @@ def test_compiled_reference_matches_golden(ref_lib, golden, case):
     U.assert_same_bytes(U.run_conv(ref_lib, case, x, k, b, kw), golden[f"conv/{case['name']}/y"], case["name"])
 
 
+@pytest.mark.parametrize("case", CS.DW_TC_CASES + CS.STEM_CASES + CS.PERSISTENT_CASES, ids=lambda c: c["name"])
+def test_oracle_matches_compiled_reference_on_device_path_cases(ref_lib, oracle_c, case):
+    """The GPU tests compare these shapes (tcgen05 depthwise classes, stem loaders, long item sequences) with the C oracle;
+    here the oracle is pinned to the unmodified reference on exactly the same inputs."""
+    x, k, b, kw = U.conv_setup(case)
+    U.assert_same_bytes(U.run_conv(oracle_c, case, x, k, b, kw), U.run_conv(ref_lib, case, x, k, b, kw), case["name"])
+
+
 def test_compiled_reference_q31_matches_oracle(ref_lib, oracle_c):
     rng = np.random.default_rng(3)
     x = rng.integers(-(2**31), 2**31, 1 << 16, dtype=np.int64).astype(np.int32)
