@@ -56,6 +56,14 @@ void qnnp_cuda_debug_set_accumulator_dump(int32_t* device_buffer);
 int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int folded, int bias_steps, int out[24]);
 int qnnp_cuda_debug_operator_is_folded(qnnp_operator_t op);
 
+/* Packed operands of the tensor-core kernel for a K x N fully-connected / 1x1 operator, built on the host; needs no GPU
+ * (tests/test_igemm_pack.py replays the UMMA algebra on these bytes).  kernel = [n][k] uint8, bias = [n] int32.
+ * meta = {folded, nkc, n_tiles, n_tile, n_mma, blk_chunks, bias_steps, b_signed, has_b2, k_tail_pad, has_corr, 0, ...};
+ * blob = per n-tile [blk_chunks][n_mma][16 B]; *blob_bytes / *bias_count: capacity in, size out.  Returns 1 / 0. */
+int qnnp_cuda_debug_pack_igemm(size_t k, size_t n, uint8_t input_zero_point, uint8_t kernel_zero_point, const uint8_t* kernel,
+                               const int32_t* bias, int meta[16], uint8_t* blob, size_t* blob_bytes, int32_t* folded_bias,
+                               size_t* bias_count);
+
 /* Tiling of the depthwise tensor-core kernel (q8_dwconv_umma_sm100.cu) for a geometry; needs no GPU.  wmode: 0 = every
  * w - kzp fits s8, 1 = kzp == 0 (u8 weights), 2 = w - kzp split into two s8 operands.
  * out = {G, mt, xt, yt, nt, nb, Q, whole, planes, box_rows, box_px, plane_tx, plane_bytes, a_bytes, b_bytes, cg_bytes,

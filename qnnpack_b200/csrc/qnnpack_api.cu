@@ -518,7 +518,10 @@ int bias_steps_needed(int32_t b) {
   return steps < 1 ? 1 : (steps > 1000000 ? 1000000 : (int) steps);
 }
 
-enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
+// Plans the tensor-core kernel for the operator and builds its packed operands in HOST memory (no CUDA call: the CPU test
+// tests/test_igemm_pack.py replays the UMMA algebra on exactly these bytes).
+enum qnnp_status pack_igemm_host(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias, std::vector<uint8_t>& blob,
+                                 std::vector<int32_t>& fbias) {
   const size_t ks = (size_t) op->kh * op->kw;
   const size_t K = ks * op->gic;
   if (K > (size_t) 1 << 24 || op->goc > (size_t) 1 << 24) {
@@ -543,8 +546,9 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
   if (mode_env != nullptr && strcmp(mode_env, "folded") == 0) want_folded = steps <= kMaxBiasSteps;
   IgemmPlan pl;
   // folded mode only when its plan keeps a healthy ring; otherwise the "ones" plan (weights may stream)
-  bool planned = want_folded && plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, 1, steps, &pl) && pl.good;
-  if (!planned) planned = plan_igemm(K, op->goc, op->groups, g_lib.max_smem_optin, 0, 0, &pl);
+  const int optin = g_lib.initialized ? g_lib.max_smem_optin : 232448;  // B200: 227 KB opt-in (CPU-side planning/tests)
+  bool planned = want_folded && plan_igemm(K, op->goc, op->groups, optin, 1, steps, &pl) && pl.good;
+  if (!planned) planned = plan_igemm(K, op->goc, op->groups, optin, 0, 0, &pl);
   if (!planned) {
     log_error("shared-memory plan failed (K=%zu, N=%zu)", K, op->goc);
     return qnnp_status_unsupported_parameter;
@@ -567,8 +571,8 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
   //   chunks [nkc, nkc+2)        constant (128 - kzp) operand, all 32 k valid
   //   chunks [nkc+2, nkc+4)      same, zero where the last chunk pair is K padding
   //   chunks [nkc+4+2t, +2)      bias digits of step t (k = 0..30: digits of Q, k = 31: e in step 0)
-  std::vector<uint8_t> blob(w_total, 0);
-  std::vector<int32_t> fbias(bias_count, 0);
+  blob.assign(w_total, 0);
+  fbias.assign(bias_count, 0);
   const uint8_t wflip = op->b_signed ? 0x80 : 0x00;
   const uint8_t b2val = (uint8_t) (int8_t) (128 - (int) op->kzp);
   for (uint32_t g = 0; g < op->groups; g++) {
@@ -612,10 +616,18 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
   }
   op->weights_bytes = w_total;
   op->bias_count = bias_count;
-  cudaError_t e = cudaMalloc(&op->d_weights, w_total);
-  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, bias_count * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, blob.data(), w_total, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), bias_count * sizeof(int32_t), cudaMemcpyHostToDevice);
+  return qnnp_status_success;
+}
+
+enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
+  std::vector<uint8_t> blob;
+  std::vector<int32_t> fbias;
+  const enum qnnp_status st = pack_igemm_host(op, kernel, bias, blob, fbias);
+  if (st != qnnp_status_success) return st;
+  cudaError_t e = cudaMalloc(&op->d_weights, blob.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, fbias.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), fbias.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   return map_cuda(e, "uploading packed weights");
 }
 
@@ -1217,6 +1229,28 @@ QNNP_EXPORT int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, i
                      p.a_off[0], p.a_off[1], p.a_off[2], p.a_off[3], p.a_off[4], p.a_lbo[0], p.a_lbo[1], p.a_lbo[2], p.a_lbo[3],
                      p.a_lbo[4], p.sbo, p.nb_cols, p.b_signed, p.acc_stride, p.cblocks, p.cgs, (int) p.total_items, 0, 0};
   for (int i = 0; i < 40; i++) out[i] = v[i];
+  return 1;
+}
+/* Packed operands of the tensor-core kernel for a K x N fully-connected / 1x1 operator, built on the host (no GPU needed).
+ * meta = {folded, nkc, n_tiles, n_tile, n_mma, blk_chunks, bias_steps, b_signed, has_b2, k_tail_pad, has_corr, 0...}.
+ * Returns 1 and fills blob / folded_bias (sizes in *blob_bytes / *bias_count; pass capacities in), 0 on failure. */
+QNNP_EXPORT int qnnp_cuda_debug_pack_igemm(size_t k, size_t n, uint8_t input_zero_point, uint8_t kernel_zero_point,
+                                           const uint8_t* kernel, const int32_t* bias, int meta[16], uint8_t* blob,
+                                           size_t* blob_bytes, int32_t* folded_bias, size_t* bias_count) {
+  qnnp_operator op;
+  op.kind = kKindIgemmGemm;
+  op.groups = 1, op.gic = k, op.goc = n;
+  op.izp = input_zero_point, op.kzp = kernel_zero_point;
+  std::vector<uint8_t> b;
+  std::vector<int32_t> fb;
+  if (pack_igemm_host(&op, kernel, bias, b, fb) != qnnp_status_success) return 0;
+  if (b.size() > *blob_bytes || fb.size() > *bias_count) return 0;
+  memcpy(blob, b.data(), b.size());
+  memcpy(folded_bias, fb.data(), fb.size() * sizeof(int32_t));
+  *blob_bytes = b.size(), *bias_count = fb.size();
+  const int v[16] = {op.folded, op.nkc, op.n_tiles, op.n_tile, op.n_mma, op.blk_chunks, op.bias_steps, op.b_signed, op.has_b2,
+                     op.k_tail_pad, op.has_corr, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 16; i++) meta[i] = v[i];
   return 1;
 }
 /* 1 if the operator runs in folded mode (bias + zero-point correction on the tensor core), 0 otherwise. */
