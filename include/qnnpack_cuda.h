@@ -71,6 +71,12 @@ int qnnp_cuda_debug_pack_igemm(size_t k, size_t n, uint8_t input_zero_point, uin
  *        total_items, 0, 0}.  Returns 1, or 0 when the shape is not eligible (the CUDA-core depthwise kernels run instead). */
 int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, int in_w, int out_h, int out_w, int stride, int pad_top,
                                 int pad_left, int wmode, int out[40]);
+/* Operands of the depthwise tensor-core kernel for `channels` (% 16 == 0) channels, built on the host; needs no GPU.
+ * kernel = [channels][9] uint8, bias = [channels] int32.  wpack receives (channels/16) * 5 * 2 * nb_cols * 16 bytes
+ * (nb_cols = 32 when the returned mode is 2, else 16), bias_cls 64 * channels int32 (XOR 2^31 when u_form != 0).
+ * Returns the weight-operand mode (0: one s8 operand, 1: u8, 2: two s8 operands) or -1. */
+int qnnp_cuda_debug_pack_dwconv(size_t channels, uint8_t input_zero_point, uint8_t kernel_zero_point, const uint8_t* kernel,
+                                const int32_t* bias, int u_form, uint8_t* wpack, int32_t* bias_cls);
 /* Launches of the depthwise tensor-core kernel since qnnp_initialize() (tests use it to prove the routing). */
 unsigned long long qnnp_cuda_debug_dw_umma_launch_count(void);
 

@@ -631,6 +631,45 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
   return map_cuda(e, "uploading packed weights");
 }
 
+// Operands of the depthwise tensor-core kernel, built in HOST memory (tests/test_dw_umma_plan.py replays the kernel on
+// exactly these bytes).  kernel = [C][9] uint8, wmode: 0 one s8 operand, 1 u8 operand (kzp == 0), 2 two s8 operands.
+//   wp: per 16-channel group and UMMA u the B operand [2 K-chunks][nbc rows][16 B], each K-chunk diag(w_tap - kzp)
+//   bc: [64 border classes][C]: bias - izp * (sum of w - kzp over the taps inside the image); uform: XOR 2^31 (the offset
+//       of the "U" requantisation rides on the bias add)
+void pack_dw_umma_host(size_t C, const uint8_t* kernel, const int32_t* bias, int izp, int kzp, int wmode, bool uform,
+                       std::vector<uint8_t>& wp, std::vector<int32_t>& bc) {
+  const int nbc = wmode == 2 ? 32 : 16;
+  const size_t ub = (size_t) 2 * nbc * 16;  // bytes of one UMMA's B operand
+  wp.assign((C / 16) * q8::kDwTcTaps * ub, 0);
+  const int t0[q8::kDwTcTaps] = {0, 3, 6, 1, 7}, t1[q8::kDwTcTaps] = {2, 5, 8, 4, -1};  // tap = ky*3 + kx
+  for (size_t cg = 0; cg < C / 16; cg++)
+    for (int u = 0; u < q8::kDwTcTaps; u++)
+      for (int ch = 0; ch < 2; ch++) {
+        const int tap = ch == 0 ? t0[u] : t1[u];
+        if (tap < 0) continue;
+        for (int n = 0; n < 16; n++) {
+          const int32_t w = kernel[(cg * 16 + n) * 9 + tap];
+          const int32_t d = w - kzp;
+          int32_t da = wmode == 1 ? w : d, db = 0;
+          if (wmode == 2) da = d >> 1, db = d - da;
+          uint8_t* blk = wp.data() + (cg * q8::kDwTcTaps + u) * ub + (size_t) ch * nbc * 16;
+          blk[(size_t) n * 16 + n] = (uint8_t) da;                        // B[n][k = n] of this K-chunk
+          if (nbc == 32) blk[(size_t) (16 + n) * 16 + n] = (uint8_t) db;  // second operand half: rows 16..31
+        }
+      }
+  bc.assign((size_t) 64 * C, 0);
+  for (int rm = 0; rm < 8; rm++)
+    for (int cm = 0; cm < 8; cm++)
+      for (size_t c = 0; c < C; c++) {
+        int64_t sum = 0;
+        for (int ky = 0; ky < 3; ky++)
+          for (int kx = 0; kx < 3; kx++)
+            if (((rm >> ky) & 1) && ((cm >> kx) & 1)) sum += (int32_t) kernel[c * 9 + ky * 3 + kx] - kzp;
+        const int32_t v = (int32_t) ((int64_t) bias[c] - (int64_t) izp * sum);
+        bc[((size_t) rm * 8 + cm) * C + c] = uform ? (int32_t) ((uint32_t) v ^ 0x80000000u) : v;
+      }
+}
+
 enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
   const size_t C = op->groups;
   op->c_pad = (int) round_up(C, 4);
@@ -678,37 +717,9 @@ enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int3
   if (e == cudaSuccess) e = cudaMemcpy(op->d_dw_wb, wb.data(), wb.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   // tensor-core kernel operands (q8_dwconv_umma_sm100.cu)
   if (e == cudaSuccess && (C % 16) == 0) {
-    const int nbc = op->dw_wmode == 2 ? 32 : 16;
-    const size_t ub = (size_t) 2 * nbc * 16;  // bytes of one UMMA's B operand: [2 K-chunks][nbc rows][16 B]
-    std::vector<uint8_t> wp((C / 16) * q8::kDwTcTaps * ub, 0);
-    const int t0[q8::kDwTcTaps] = {0, 3, 6, 1, 7}, t1[q8::kDwTcTaps] = {2, 5, 8, 4, -1};  // tap = ky*3 + kx
-    for (size_t cg = 0; cg < C / 16; cg++)
-      for (int u = 0; u < q8::kDwTcTaps; u++)
-        for (int ch = 0; ch < 2; ch++) {
-          const int tap = ch == 0 ? t0[u] : t1[u];
-          if (tap < 0) continue;
-          for (int n = 0; n < 16; n++) {
-            const int32_t d = w32[(size_t) tap * op->c_pad + cg * 16 + n];
-            int32_t da = op->dw_wmode == 1 ? (int32_t) kernel[(cg * 16 + n) * 9 + tap] : d, db = 0;
-            if (op->dw_wmode == 2) da = d >> 1, db = d - da;
-            uint8_t* blk = wp.data() + (cg * q8::kDwTcTaps + u) * ub + (size_t) ch * nbc * 16;
-            blk[(size_t) n * 16 + n] = (uint8_t) da;                               // B[n][k = n] of this K-chunk
-            if (nbc == 32) blk[(size_t) (16 + n) * 16 + n] = (uint8_t) db;         // second operand half: rows 16..31
-          }
-        }
-    // bias per border class: rows/columns of the 3x3 window that fall inside the image are bits of rm / cm
-    std::vector<int32_t> bc((size_t) 64 * C);
-    const bool uform = op->rq_mode == 5 || op->rq_mode == 6;
-    for (int rm = 0; rm < 8; rm++)
-      for (int cm = 0; cm < 8; cm++)
-        for (size_t c = 0; c < C; c++) {
-          int64_t sum = 0;
-          for (int ky = 0; ky < 3; ky++)
-            for (int kx = 0; kx < 3; kx++)
-              if (((rm >> ky) & 1) && ((cm >> kx) & 1)) sum += w32[(size_t) (ky * 3 + kx) * op->c_pad + c];
-          const int32_t v = (int32_t) ((int64_t) bias[c] - (int64_t) op->izp * sum);
-          bc[((size_t) rm * 8 + cm) * C + c] = uform ? (int32_t) ((uint32_t) v ^ 0x80000000u) : v;
-        }
+    std::vector<uint8_t> wp;
+    std::vector<int32_t> bc;
+    pack_dw_umma_host(C, kernel, bias, op->izp, op->kzp, op->dw_wmode, op->rq_mode == 5 || op->rq_mode == 6, wp, bc);
     e = cudaMalloc((void**) &op->d_dwtc_w, wp.size());
     if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_dwtc_bias, bc.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_w, wp.data(), wp.size(), cudaMemcpyHostToDevice);
@@ -1252,6 +1263,26 @@ QNNP_EXPORT int qnnp_cuda_debug_pack_igemm(size_t k, size_t n, uint8_t input_zer
                      op.k_tail_pad, op.has_corr, 0, 0, 0, 0, 0};
   for (int i = 0; i < 16; i++) meta[i] = v[i];
   return 1;
+}
+/* Operands of the depthwise tensor-core kernel for C channels (C % 16 == 0), built on the host; needs no GPU.
+ * wpack: (C/16) * 5 * 2 * nb_cols * 16 bytes (nb_cols = 32 for wmode 2, else 16); bias_cls: 64 * C int32.
+ * Returns the weight-operand mode (0 / 1 / 2) the library would choose, or -1. */
+QNNP_EXPORT int qnnp_cuda_debug_pack_dwconv(size_t channels, uint8_t input_zero_point, uint8_t kernel_zero_point,
+                                            const uint8_t* kernel, const int32_t* bias, int u_form, uint8_t* wpack,
+                                            int32_t* bias_cls) {
+  if (channels == 0 || (channels % 16) != 0) return -1;
+  bool fits_s8 = true;
+  for (size_t i = 0; i < channels * 9; i++) {
+    const int d = (int) kernel[i] - (int) kernel_zero_point;
+    if (d < -128 || d > 127) fits_s8 = false;
+  }
+  const int wmode = kernel_zero_point == 0 ? 1 : (fits_s8 ? 0 : 2);
+  std::vector<uint8_t> wp;
+  std::vector<int32_t> bc;
+  pack_dw_umma_host(channels, kernel, bias, input_zero_point, kernel_zero_point, wmode, u_form != 0, wp, bc);
+  memcpy(wpack, wp.data(), wp.size());
+  memcpy(bias_cls, bc.data(), bc.size() * sizeof(int32_t));
+  return wmode;
 }
 /* 1 if the operator runs in folded mode (bias + zero-point correction on the tensor core), 0 otherwise. */
 QNNP_EXPORT int qnnp_cuda_debug_operator_is_folded(qnnp_operator_t op) { return op != nullptr && op->folded ? 1 : 0; }

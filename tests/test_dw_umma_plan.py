@@ -192,6 +192,93 @@ def test_ineligible_shapes_fall_back(plan):
     assert plan(16, 1, 9, 9, 2)[0] is None      # stride 2 needs an even width
 
 
+def replay_packed(d, x, wpack, bias_cls, signed_b, s, pad, oh, ow):
+    """Like replay(), but with the library's own packed operands: every UMMA multiplies the two 16-byte K-chunks the
+    descriptors address (the empty tap slot included: its LBO is 0 and its weights must be zero) with the B block
+    [2 chunks][nb_cols rows][16 B] of (channel group, u); the epilogue adds the two operand halves and bias_cls."""
+    n, h, w, c = x.shape
+    nbc = d["nb_cols"]
+    ub = 2 * nbc * 16
+    acc = np.zeros((n, oh, ow, c), dtype=np.int64)
+    for item in range(d["total_items"]):
+        r, cb = divmod(item, d["cblocks"])
+        q, xtile = divmod(r, d["xt"])
+        nblk, ytile = divmod(q, d["yt"])
+        n0, oy0, ox0 = nblk * d["nb"], ytile * 16, xtile * d["mt"] * 8
+        mt_eff = min(d["mt"], (ow - ox0 + 7) // 8)
+        g_eff = min(d["G"], d["cgs"] - cb * d["G"])
+        y0 = (0 if d["whole"] else oy0 * s) - pad[0]
+        for gi in range(g_eff):
+            cg = cb * d["G"] + gi
+            smem = np.zeros(d["a_bytes"] + 64 * 1024, dtype=np.uint8)
+            for par in range(d["planes"]):
+                xo = ox0 + (d["x_org0"], d["x_org1"])[par]
+                box = np.zeros((d["nb"], d["box_rows"], d["box_px"], 16), dtype=np.uint8)
+                for i in range(d["nb"]):
+                    for ry in range(d["box_rows"]):
+                        for rx in range(d["box_px"]):
+                            iy = y0 + ry
+                            ix = (xo + rx) if s == 1 else 2 * (xo + rx) + par
+                            inb = (xo + rx) >= 0 and ((xo + rx) < w if s == 1 else (xo + rx) < w // 2)
+                            if n0 + i < n and 0 <= iy < h and inb and 0 <= ix < w:
+                                box[i, ry, rx] = x[n0 + i, iy, ix, cg * 16:cg * 16 + 16]
+                smem[par * d["plane_bytes"]:par * d["plane_bytes"] + d["plane_tx"]] = box.reshape(-1)
+            for j in range(mt_eff):
+                a = np.zeros((128, nbc), dtype=np.int64)
+                for u in range(5):
+                    blk = wpack[(cg * 5 + u) * ub:(cg * 5 + u + 1) * ub].reshape(2, nbc, 16)
+                    bmat = (blk.view(np.int8) if signed_b else blk).astype(np.int64)
+                    for ch in range(2):
+                        base = d["a_off%d" % u] + ch * d["a_lbo%d" % u] + j * 128
+                        rows = np.stack([smem[base + (m // 8) * d["sbo"] + (m % 8) * 16:][:16] for m in range(128)])
+                        a += rows.astype(np.int64) @ bmat[ch].T
+                for m in range(128):
+                    g, px = divmod(m, 8)
+                    img, oyl = divmod(g, d["Q"])
+                    nn, oy, ox = n0 + img, oy0 + oyl, ox0 + 8 * j + px
+                    if not (img < d["nb"] and nn < n and oy < oh and ox < ow):
+                        continue
+                    iy0, ix0 = oy * s - pad[0], ox * s - pad[1]
+                    rm = sum(1 << ky for ky in range(3) if 0 <= iy0 + ky < h)
+                    cm = sum(1 << kx for kx in range(3) if 0 <= ix0 + kx < w)
+                    v = a[m, :16] + (a[m, 16:32] if nbc == 32 else 0)
+                    acc[nn, oy, ox, cg * 16:cg * 16 + 16] = v + bias_cls[rm * 8 + cm, cg * 16:cg * 16 + 16]
+    return acc
+
+
+@pytest.mark.parametrize("kzp,izp", [(127, 131), (128, 7), (0, 255), (255, 0), (1, 128)])
+@pytest.mark.parametrize("c,n,h,w,s,pad", [(32, 2, 12, 13, 1, (1, 1)), (16, 3, 14, 14, 2, (1, 1)), (48, 2, 7, 7, 1, (1, 1)),
+                                            (16, 1, 22, 10, 2, (0, 1))])
+def test_kernel_replay_on_the_packed_operands(plan, c, n, h, w, s, pad, kzp, izp):
+    """End to end on the host: the bytes pack_dw_umma_host produces (diagonal B blocks, operand split, border-class
+    biases) + the planner's addressing reproduce the reference accumulators for every weight-operand mode."""
+    from qnnpack_b200 import build
+    lib = C.CDLL(build.build())
+    lib.qnnp_cuda_debug_pack_dwconv.argtypes = [C.c_size_t, C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_void_p]
+    rng = np.random.default_rng(c + h + kzp)
+    wk = rng.integers(0, 256, (c, 9), dtype=np.uint8)
+    if kzp not in (0, 128):
+        wk[0, 0], wk[-1, 8] = 0, 255                    # make sure the 9-bit range of w - kzp is really used
+    bias = rng.integers(-50000, 50000, c).astype(np.int32)
+    wpack = np.zeros((c // 16) * 5 * 2 * 32 * 16, dtype=np.uint8)
+    bias_cls = np.zeros((64, c), dtype=np.int32)
+    wmode = lib.qnnp_cuda_debug_pack_dwconv(c, izp, kzp, wk.ctypes.data, bias.ctypes.data, 0, wpack.ctypes.data,
+                                            bias_cls.ctypes.data)
+    dmin, dmax = int(wk.min()) - kzp, int(wk.max()) - kzp
+    assert wmode == (1 if kzp == 0 else 0 if (dmin >= -128 and dmax <= 127) else 2)
+    oh, ow = (h + 2 * pad[0] - 3) // s + 1, (w + 2 * pad[1] - 3) // s + 1
+    d = plan(c, n, h, w, s, pad, wmode)[0]
+    assert d is not None and d["nb_cols"] == (32 if wmode == 2 else 16) and d["b_signed"] == (0 if wmode == 1 else 1)
+    x = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+    got = replay_packed(d, x, wpack, bias_cls.astype(np.int64), wmode != 1, s, pad, oh, ow)
+    assert np.array_equal(got, direct(x, wk, bias.astype(np.int64), izp, kzp, s, pad, oh, ow))
+    # the "U" requantisation offset rides on the same table
+    bias_u = np.zeros((64, c), dtype=np.int32)
+    lib.qnnp_cuda_debug_pack_dwconv(c, izp, kzp, wk.ctypes.data, bias.ctypes.data, 1, wpack.ctypes.data, bias_u.ctypes.data)
+    assert np.array_equal(bias_u.view(np.uint32), bias_cls.view(np.uint32) ^ np.uint32(0x80000000))
+
+
 def test_item_stepping_is_equivalent_to_decoding():
     """Model of the kernel's item walk (q8_dwconv_umma_sm100.cu: first_pos / advance_pos with the host's step digits):
     a CTA's k-th item, reached by adding the grid size in (cb, xtile, ytile, nblk) digits with carries, must be the item
