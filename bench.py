@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=0, help="reference arm: images per step (0 = 2 per thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     return ap.parse_args()
 
 
@@ -289,6 +290,21 @@ def b200_main(args, rank, local_rank, world):
         # restore the stem's input for anything that runs afterwards
         lib.setup_convolution(stem_op, B, stem.h, stem.h, x_in.data_ptr(), stem.cin, buf_a.data_ptr(), stem.cout)
 
+    # ---- parity gate on the benchmarked configuration (outside every timed region) -------------------------------
+    # The step is run once more, exactly as timed (device pointers, asynchronous launches, same batch); the first, second,
+    # middle and last image's slice of EVERY layer's output is copied back right after that layer and compared byte for
+    # byte with the unmodified reference (oracle/_ref) pushed through the same operators image by image.
+    parity = None
+    if not args.no_parity_check:
+        from oracle import chain_check as CC
+        images = sorted({0, 1 % B, B // 2 - 1 if B >= 2 else 0, B - 1})
+        parity = CC.check_device_stack(stack, params, B, x_in, buf_a, buf_b, images,
+                                       log=lambda m: print(m, file=sys.stderr, flush=True))
+        parity["rank"] = rank
+        if parity["mismatches"] != 0:
+            print(f"bench.py: PARITY FAILURE on rank {rank}: {json.dumps(parity)}", file=sys.stderr, flush=True)
+            os._exit(3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,7 +378,7 @@ def b200_main(args, rank, local_rank, world):
                    "l2": "every layer streams activations far larger than the 126 MB L2 (no flush needed)",
                    "quantization": "zero points 127, requant scale 1/(128*sqrt(K)), clamp 0..255",
                    "weights_broadcast_bytes": bcast_bytes},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity,
         "roofline": roofline, "cpu_baseline": cpu, "q8gemm_sweep": q8gemm, "per_kernel": per_kernel, "layers": layers_out,
         "stack_ops_g": stack.total_ops(B) / 1e9, "stack_algorithmic_gb": stack.total_bytes(B) / 1e9,
         "stack_frac_of_hbm_roofline": (stack.total_bytes(B) / 1e6 / peak_gbs) / ms_per_step,

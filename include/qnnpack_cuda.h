@@ -80,6 +80,14 @@ int qnnp_cuda_debug_pack_dwconv(size_t channels, uint8_t input_zero_point, uint8
 /* Launches of the depthwise tensor-core kernel since qnnp_initialize() (tests use it to prove the routing). */
 unsigned long long qnnp_cuda_debug_dw_umma_launch_count(void);
 
+/* Panel-epilogue tables of the tensor-core kernel for an n-tile (CPU-callable; tests/test_planner.py replays them). */
+void qnnp_cuda_debug_panel_tables(int n_tile, int mt, int folded, int out[50]);
+
+/* Measured dense int8 tensor-core peak of this device in tera-ops/s: a shared-memory-resident tcgen05.mma kind::i8 loop
+ * (148 CTAs x `iters` x 8 UMMAs of 128x256x32), `reps` launches timed with CUDA events on the library's stream.  The
+ * denominator of "%-of-peak on q8gemm" (BASELINE.json metric; reference counter bench/q8gemm.cc:108). */
+enum qnnp_status qnnp_cuda_measure_int8_peak(int iters, int reps, double* tops, double* ms_per_launch);
+
 /* Name of the kernel family an operator was routed to: "igemm-gemm", "igemm-conv", "dwconv3x3", "direct". */
 const char* qnnp_cuda_operator_kernel_name(qnnp_operator_t op);
 

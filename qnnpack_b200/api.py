@@ -16,7 +16,8 @@ import numpy as np
 from . import _capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(HERE, "lib", "libqnnpack.so")
+# QNNP_LIB_PATH selects another build of the same library (A/B runs of compile-time variants)
+PRODUCT_LIB = os.environ.get("QNNP_LIB_PATH") or os.path.join(HERE, "lib", "libqnnpack.so")
 
 
 class QnnpackError(RuntimeError):
@@ -139,6 +140,15 @@ class QnnpackLibrary:
         if st != 0:
             raise QnnpackError("qnnp_cuda_operator_packed_bias", st)
         return p.value, n.value
+
+    def measure_int8_peak(self, iters: int = 2000, reps: int = 5):
+        """-> (tera-ops/s, ms per launch): smem-resident tcgen05 kind::i8 loop on every SM (q8_peak_sm100.cu)."""
+        tops, ms = C.c_double(), C.c_double()
+        self.lib.qnnp_cuda_measure_int8_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        st = self.lib.qnnp_cuda_measure_int8_peak(iters, reps, C.byref(tops), C.byref(ms))
+        if st != 0:
+            raise QnnpackError("qnnp_cuda_measure_int8_peak", st)
+        return tops.value, ms.value
 
     def set_stream(self, cuda_stream: int):
         st = self.lib.qnnp_cuda_set_stream(C.c_void_p(cuda_stream))

@@ -93,7 +93,8 @@ struct DirectParams {
 
 cudaError_t launch_q8_dwconv3x3(DwParams p, int cv, cudaStream_t stream);
 cudaError_t launch_q8_dwconv3x3_stream(DwStreamParams p, cudaStream_t stream);
-cudaError_t launch_q8_dwconv3x3_umma(const DwTcParams& p, const void* tensor_map, int grid, cudaStream_t stream);
+cudaError_t launch_q8_dwconv3x3_umma(const DwTcParams& p, const void* tensor_map, int grid, int max_smem_optin,
+                                     cudaStream_t stream);
 cudaError_t launch_q8_direct_conv(const DirectParams& p, cudaStream_t stream);
 cudaError_t launch_q8_requantize(const int32_t* in, uint8_t* out, long long n, const Q8Requant& rq, cudaStream_t stream);
 

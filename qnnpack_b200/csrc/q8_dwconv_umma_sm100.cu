@@ -29,6 +29,7 @@
 // Same integers as the reference:  acc[c] = bias[c] + sum_valid_taps (a_tap[c] - izp) * (w_tap[c] - kzp).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -182,59 +183,68 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
   if (valid) *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// UMMA-issuing role of warp kMmaWarp + w: lane 0 alone runs the loop.  (Keeping the whole warp in the loop and
-// predicating only the tcgen05 instructions is far worse: nvcc wraps every tcgen05.mma in an elect/broadcast loop that
-// then iterates once per ACTIVE lane — measured 3x slower.)
+// UMMA-issuing role of warp kMmaWarp + w.  The whole warp walks the loop CONVERGED and every operand is warp-uniform by
+// construction (kernel parameters, blockIdx, loop counters, values broadcast with __shfl_sync), so descriptors and
+// addresses live in uniform registers and a tcgen05.mma costs its operand arithmetic plus one instruction; an elected
+// lane issues.  (Round 1 put the loop under `if (lane == 0)`: nvcc then rebuilt every operand in vector registers and
+// moved it across with an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, ~30 instructions per UMMA — 17 % of all the
+// instructions this kernel executed, profiles/r1h_dwconv_umma_first2.)
 template <int NB>
-__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t smem_base, uint32_t tmem_base, int lane, int w,
+__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t smem_base_v, uint32_t tmem_base_v, int w_v,
                                          uint32_t first, uint32_t step, uint32_t total) {
-    if (lane == 0) {
-      const uint32_t tmem_u = tmem_base;
-      const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
-      uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
+  const int w = __shfl_sync(0xffffffffu, w_v, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base_v, 0);
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_base_v, 0);
+  const uint32_t ctl_u = __shfl_sync(0xffffffffu, smem_u32(&ctl), 0);
+  const uint32_t bar_full = ctl_u + (uint32_t) offsetof(Ctl, full), bar_empty = ctl_u + (uint32_t) offsetof(Ctl, empty);
+  const uint32_t bar_tfull = ctl_u + (uint32_t) offsetof(Ctl, tmem_full), bar_tempty = ctl_u + (uint32_t) offsetof(Ctl, tmem_empty);
+  const uint32_t idesc = umma_idesc_i8(128, NB, false, p.b_signed != 0);
+  uint64_t adesc[kDwTcTaps], bdesc[kDwTcTaps];
+#pragma unroll
+  for (int u = 0; u < kDwTcTaps; u++) {
+    adesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], (uint32_t) p.sbo);
+    bdesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 128);
+  }
+  int stage = 0, as = 0;
+  uint32_t phase = 0, as_phase = 0;
+  ItemPos pos = first_pos(p, first);
+  for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
+    const DwItem it = make_item(p, pos);
+    const int units = it.mt_eff * it.g_eff;
+    const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
+    // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
+    uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
+    const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
+#pragma unroll
+    for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
+      int j, gi;
+      unit_split(w + i * kMmaWarps, it.mt_eff, inv, j, gi);
+      b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
+      a16[i] = b16[i] + (uint32_t) j * 8;
+      dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
+    }
+    mbar_wait(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
+    mbar_wait(bar_full + 8u * (uint32_t) stage, phase);
+    tc_fence_after_sync();
+    if (elect_one()) {
+      // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
+      // outer loop, so consecutive instructions hit different accumulators
 #pragma unroll
       for (int u = 0; u < kDwTcTaps; u++) {
-        adesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], (uint32_t) p.sbo);
-        bdesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 128);
-      }
-      int stage = 0, as = 0;
-      uint32_t phase = 0, as_phase = 0;
-      ItemPos pos = first_pos(p, first);
-      for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
-        const DwItem it = make_item(p, pos);
-        const int units = it.mt_eff * it.g_eff;
-        const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
-        // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
-        uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
-        const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
 #pragma unroll
         for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
-          int j, gi;
-          unit_split(w + i * kMmaWarps, it.mt_eff, inv, j, gi);
-          b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
-          a16[i] = b16[i] + (uint32_t) j * 8;
-          dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
+          if (w + i * kMmaWarps < units)
+            umma_i8(tmem_u + dcol[i], adesc[u] + a16[i], bdesc[u] + b16[i], idesc, u > 0 ? 1u : 0u);
         }
-        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
-        mbar_wait(smem_u32(&ctl.full[stage]), phase);
-        tc_fence_after_sync();
-        // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
-        // outer loop, so consecutive instructions hit different accumulators
-#pragma unroll
-        for (int u = 0; u < kDwTcTaps; u++) {
-#pragma unroll
-          for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
-            if (w + i * kMmaWarps < units)
-              umma_i8(tmem_u + dcol[i], adesc[u] + a16[i], bdesc[u] + b16[i], idesc, u > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(smem_u32(&ctl.empty[stage]));    // smem stage may be refilled once these UMMAs have read it
-        umma_commit(smem_u32(&ctl.tmem_full[as]));   // this warp's share of the accumulators is complete
-        if (++stage == p.num_stages) stage = 0, phase ^= 1;
-        as ^= 1;
-        if (as == 0) as_phase ^= 1;
       }
+      umma_commit(bar_empty + 8u * (uint32_t) stage);  // smem stage may be refilled once these UMMAs have read it
+      umma_commit(bar_tfull + 8u * (uint32_t) as);     // this warp's share of the accumulators is complete
     }
+    __syncwarp();
+    if (++stage == p.num_stages) stage = 0, phase ^= 1;
+    as ^= 1;
+    if (as == 0) as_phase ^= 1;
+  }
 }
 
 template <int S, int RQ, int NB>
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // concurrently (1 -> 4 warps: 2x faster; 4 -> 7: another 2-5 %); warp w owns the units w, w+7, ... of every item.
     // (ONE copy of the loop for all of them: per-warp template instances multiply the code and were measured 2.3x slower,
     // presumably instruction-cache misses)
-    mma_role<NB>(p, ctl, smem_base, tmem_base, lane, warp - kMmaWarp, first, step, total);
+    mma_role<NB>(p, ctl, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
   } else {
     // ===================================== epilogue (16 warps) =====================================
     const int q = warp & 3, h = warp >> 2;
@@ -367,32 +377,34 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 template <int S, int RQ, int NB>
-cudaError_t launch_one(const DwTcParams& p, const CUtensorMap& tm, int grid, cudaStream_t stream) {
+cudaError_t launch_one(const DwTcParams& p, const CUtensorMap& tm, int grid, int max_smem_optin, cudaStream_t stream) {
   auto kern = q8_dwconv3x3_umma_kernel<S, RQ, NB>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total);
-  if (e != cudaSuccess) return e;
+  // once per instantiation, to the device maximum (a per-launch value raced between host threads; see the igemm launcher)
+  static cudaError_t attr_status = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+  if (attr_status != cudaSuccess) return attr_status;
   kern<<<grid, kThreads, p.smem_total, stream>>>(p, tm);
   return cudaGetLastError();
 }
 
 template <int S, int NB>
-cudaError_t launch_rq(const DwTcParams& p, const CUtensorMap& tm, int grid, cudaStream_t stream) {
+cudaError_t launch_rq(const DwTcParams& p, const CUtensorMap& tm, int grid, int max_smem_optin, cudaStream_t stream) {
   switch (p.rq_mode) {
-    case 5: return launch_one<S, 5, NB>(p, tm, grid, stream);
-    case 6: return launch_one<S, 6, NB>(p, tm, grid, stream);
-    default: return launch_one<S, 3, NB>(p, tm, grid, stream);  // generic q8_requant(): every other mode
+    case 5: return launch_one<S, 5, NB>(p, tm, grid, max_smem_optin, stream);
+    case 6: return launch_one<S, 6, NB>(p, tm, grid, max_smem_optin, stream);
+    default: return launch_one<S, 3, NB>(p, tm, grid, max_smem_optin, stream);  // generic q8_requant(): every other mode
   }
 }
 
 }  // namespace
 
-cudaError_t launch_q8_dwconv3x3_umma(const DwTcParams& p, const void* tensor_map, int grid, cudaStream_t stream) {
+cudaError_t launch_q8_dwconv3x3_umma(const DwTcParams& p, const void* tensor_map, int grid, int max_smem_optin,
+                                     cudaStream_t stream) {
   alignas(64) CUtensorMap tm;
   memcpy(&tm, tensor_map, sizeof(tm));
   if (p.stride == 1) {
-    return p.nb_cols == 32 ? launch_rq<1, 32>(p, tm, grid, stream) : launch_rq<1, 16>(p, tm, grid, stream);
+    return p.nb_cols == 32 ? launch_rq<1, 32>(p, tm, grid, max_smem_optin, stream) : launch_rq<1, 16>(p, tm, grid, max_smem_optin, stream);
   }
-  return p.nb_cols == 32 ? launch_rq<2, 32>(p, tm, grid, stream) : launch_rq<2, 16>(p, tm, grid, stream);
+  return p.nb_cols == 32 ? launch_rq<2, 32>(p, tm, grid, max_smem_optin, stream) : launch_rq<2, 16>(p, tm, grid, max_smem_optin, stream);
 }
 
 }  // namespace q8

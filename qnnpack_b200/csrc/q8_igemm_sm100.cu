@@ -30,7 +30,10 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <string.h>
+
+#include <type_traits>
 
 #include "q8_igemm_sm100.cuh"
 #include "requant_dev.cuh"
@@ -643,11 +646,131 @@ __device__ __forceinline__ void epilogue_dispatch(const IgemmParams& p, const It
 }
 
 // ------------------------------------------------------------------------------------------------
+// panel epilogue (out_mode 2)
+// ------------------------------------------------------------------------------------------------
+// Measured on the round-1 kernel (ncu source view, profiles/r1h_igemm_first3): the epilogue warps are busy ~90 % of
+// the time and only 152 of the ~260 instructions they execute per 32-column unit are the requantisation itself; the
+// rest was per-unit scaffolding (item/tail/alignment cases, address arithmetic, re-convergence), and the two IMAD.HI
+// per value keep the half-rate "heavy" FMA pipe busier (64 %) than any other unit.  This path has no cases at all:
+//   * every item — full, tail, ragged N, strided output — leaves through swizzled smem panels and 2-D tensor stores
+//     (the TMA clips rows >= M and columns >= N), so the unit loop is  load - requantise - two 16-byte stores;
+//   * panel pitches are 128/64/32/16 bytes with the matching TMA swizzle: the 8 lanes of a store phase always hit 8
+//     different 16-byte bank groups (the dense N-byte pitch gave 2- to 8-way conflicts for N = 96 ... 1280);
+//   * the final arithmetic shift alternates between IMAD.HI (heavy FMA pipe, 4 cycles per warp) and SHF (ALU pipe,
+//     2 cycles), which balances the two pipes at ~6 cycles per 32 values instead of 8 on the FMA pipe alone.
+template <int RQ, bool FOLDED>
+__device__ __forceinline__ void epi2_requant16(const IgemmParams& p, const int32_t* v, uint32_t* w) {
+  const uint32_t m2 = p.rq.u_m2, flip = FOLDED ? 0x80000000u : 0u;  // ("ones" mode: the offset rides on the bias add)
+  const uint64_t k2 = p.rq.u_k2;
+  const int32_t sm = p.rq.u_sm, sh = p.rq.shift;
+  auto rq = [&](int32_t n, bool mul) -> int32_t {
+    const uint32_t nu = (uint32_t) n ^ flip;
+    const uint32_t hi = (uint32_t) (((uint64_t) nu * m2 + k2) >> 32);
+    const int32_t t = (int32_t) (hi + (nu >> 31));
+    int32_t y = mul ? __mulhi(t, sm) : (t >> sh);  // same value (sm = 2^(32 - sh)), different pipe
+    if constexpr (RQ == 6) y = min(max(y, p.rq.qmin), p.rq.qmax);
+    return y;
+  };
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+    w[t] = pack_sat_u8x4(rq(v[4 * t], true), rq(v[4 * t + 1], false), rq(v[4 * t + 2], true), rq(v[4 * t + 3], false));
+}
+
+// One unit: W accumulator columns of the warp's 32 rows.  a0 = swizzled smem address of the unit's first 16-byte chunk in
+// this lane's staging row (the second chunk of a 32-column unit is a0 ^ 16: units start on 32-byte boundaries).
+template <int RQ, int W, bool FOLDED>
+__device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, uint32_t rs_taddr, uint32_t bias_addr, uint32_t a0,
+                                          bool first, bool last, uint32_t tmem_empty_bar, uint32_t out_free_bar,
+                                          uint32_t out_free_parity) {
+  int32_t v[W];
+  if constexpr (W == 32) {
+    tmem_ld32(taddr, v);
+  } else {
+    tmem_ld16(taddr, v);
+  }
+  int32_t rowsum = 0;
+  if constexpr (!FOLDED) tmem_ld1(rs_taddr, rowsum);
+  tmem_ld_wait();
+  if (last) {  // this warp has read all it needs from the accumulator stage: the UMMA warps may refill it
+    tc_fence_before_sync();
+    mbar_arrive(tmem_empty_bar);
+  }
+  if constexpr (!FOLDED) {
+    const int32_t corr = (int32_t) ((uint32_t) (-p.kzp * rowsum) + 0x80000000u);  // "U" offset rides on the bias add
+#pragma unroll
+    for (int t = 0; t < W / 4; t++) {
+      int4 b;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(bias_addr + 16 * t));
+      v[4 * t + 0] += b.x + corr;
+      v[4 * t + 1] += b.y + corr;
+      v[4 * t + 2] += b.z + corr;
+      v[4 * t + 3] += b.w + corr;
+    }
+  }
+  uint32_t w[W / 4];
+  epi2_requant16<RQ, FOLDED>(p, v, w);
+  if constexpr (W == 32) epi2_requant16<RQ, FOLDED>(p, v + 16, w + 4);
+  if (first) mbar_wait(out_free_bar, out_free_parity);  // the tensor stores of the pair's previous item have read staging
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  if constexpr (W == 32)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0 ^ 16u), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+// All units of one item for warp (quarter q, half): the two warps of a quarter take alternate units of the item's
+// (sub-tile, column block) sequence.  Everything that does not change inside the loop is an argument.
+template <int RQ, bool FOLDED>
+__device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint32_t tlane, uint32_t bias_base, uint32_t staging,
+                                          uint32_t row, int half, uint32_t tmem_empty_bar, uint32_t out_free_bar,
+                                          uint32_t out_free_parity) {
+  constexpr int W = FOLDED ? 32 : 16;
+  const int full = p.n_tile / W;
+  const int per_sub = full + ((p.n_tile % W) ? 1 : 0);  // (W == 32: a 16-column remainder unit when n_tile % 32 == 16)
+  const int units = mt_eff * per_sub;
+  if (half >= units) {  // a single-unit item: nothing for the second warp of the quarter
+    tc_fence_before_sync();
+    mbar_arrive(tmem_empty_bar);
+    return;
+  }
+  int c = half, j = 0;
+  if (c >= per_sub) c -= per_sub, j = 1;  // (per_sub == 1)
+  uint32_t jrow = (uint32_t) j * kTileM + row;
+  uint32_t tsub = tlane + (uint32_t) (j * p.n_mma);
+#pragma unroll 1
+  for (int u = half; u < units; u += 2) {
+    const bool first = u == half, last = u + 2 >= units;
+    // staging address of the unit's first chunk: panel base + row pitch, chunk bits swizzled like the panel's TMA mode
+    const uint2 ent = p.e2_unit[c];
+    const uint32_t pitch = ent.y & 0xFFu, lsh = (ent.y >> 8) & 0xFFu, mask = ent.y >> 16;
+    const uint32_t a0 = (staging + ent.x + jrow * pitch) ^ ((row << lsh) & mask);
+    const uint32_t taddr = tsub + (uint32_t) (c * W);
+    if (c < full) {
+      epi2_unit<RQ, W, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, first, last, tmem_empty_bar,
+                               out_free_bar, out_free_parity);
+    } else {
+      epi2_unit<RQ, 16, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, first, last, tmem_empty_bar,
+                                out_free_bar, out_free_parity);
+    }
+    c += 2;
+    if (c >= per_sub) {
+      c -= per_sub;
+      jrow += kTileM;
+      tsub += (uint32_t) p.n_mma;
+      if (c >= per_sub) {  // (per_sub == 1: both warps advance one sub-tile per unit... two per step)
+        c -= per_sub;
+        jrow += kTileM;
+        tsub += (uint32_t) p.n_mma;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(kThreads, 1)
-    q8_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_a) {
+    q8_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ IgemmStoreMaps smaps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ SmemCtl ctl;
 
@@ -790,19 +913,31 @@ __global__ void __launch_bounds__(kThreads, 1)
     cp_async_wait_all();
   } else if (warp >= kMmaWarp && warp < kMmaWarp + kMmaWarps) {
     // ===================================== UMMA issue =====================================
-    if ((tid & 31) == 0) {
-      const int w = warp - kMmaWarp;
+    // The whole warp walks the loop CONVERGED and every operand below is warp-uniform by construction (kernel
+    // parameters, blockIdx, loop counters, values broadcast with __shfl_sync), so the compiler keeps descriptors and
+    // addresses in uniform registers and a tcgen05.mma costs its operand arithmetic plus ONE instruction; one elected
+    // lane issues.  (With a single-lane branch around the loop nvcc had to rebuild every operand in a vector register
+    // and move it across with an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall: ~30 instructions per UMMA.)
+    {
+      const int w = __shfl_sync(0xffffffffu, warp - kMmaWarp, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_base, 0);
+      const uint32_t ctl_u = __shfl_sync(0xffffffffu, smem_u32(&ctl), 0);
+      const uint32_t bar_full = ctl_u + (uint32_t) offsetof(SmemCtl, full), bar_empty = ctl_u + (uint32_t) offsetof(SmemCtl, empty);
+      const uint32_t bar_tfull = ctl_u + (uint32_t) offsetof(SmemCtl, tmem_full);
+      const uint32_t bar_tempty = ctl_u + (uint32_t) offsetof(SmemCtl, tmem_empty);
+      const uint32_t b_smem_u = smem_u + p.smem_b_off, a_smem_u = smem_u + p.smem_a_off;
       const uint32_t idesc_main = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, p.b_signed != 0);
       const uint32_t idesc_us = umma_idesc_i8(kTileM, (uint32_t) p.n_mma, false, true);  // u8 x s8
       const uint32_t b_lbo = (uint32_t) p.n_mma * 16;
       const uint32_t sub_bytes = (uint32_t) p.skc * kChunkBytes;
-      const uint32_t a_const = smem_base + p.smem_aconst_off;
+      const uint32_t a_const = smem_u + p.smem_aconst_off;
       // descriptor templates (strides, version); the 16-byte-granular start address is added per use — every operand
       // lies below 256 KB, so the 14-bit address field cannot carry into its neighbours
       const uint64_t a_tmpl = umma_desc_kmajor_noswizzle(0, kChunkBytes, 128);
       const uint64_t b_tmpl = umma_desc_kmajor_noswizzle(0, b_lbo, 128);
       if (p.b_resident) {
-        mbar_wait(smem_u32(&ctl.b_full), 0);
+        mbar_wait(ctl_u + (uint32_t) offsetof(SmemCtl, b_full), 0);
         fence_proxy_async_smem();
       }
       int stage = 0;
@@ -813,51 +948,54 @@ __global__ void __launch_bounds__(kThreads, 1)
         const Item it = decode_item(p, item);
         if (++as == p.acc_stages) as = 0;
         as_phase ^= (as == 0);
-        mbar_wait(smem_u32(&ctl.tmem_empty[as]), as_phase ^ 1);
+        mbar_wait(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
+        const uint32_t d_tmem = tmem_u + as * p.acc_stride;
         // base of this (group, n_tile)'s resident block: [B1: nkc][B2 full: 2][B2 tail: 2][bias digits: 2 per step]
-        const uint32_t blk = b_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.blk_chunks) * b_lbo;
+        const uint32_t blk = b_smem_u + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.blk_chunks) * b_lbo;
         for (int ks = 0; ks < p.k_stages; ks++) {
-          mbar_wait(smem_u32(&ctl.full[stage]), phase);
+          mbar_wait(bar_full + 8u * (uint32_t) stage, phase);
           fence_proxy_async_smem();
           tc_fence_after_sync();
-          const uint32_t a_stage = a_smem + stage * p.stage_bytes;
+          const uint32_t a_stage = a_smem_u + stage * p.stage_bytes;
           int cs = p.nkc - ks * p.skc;
           cs = cs < p.skc ? cs : p.skc;
           const uint32_t b_base = p.b_resident ? blk + (uint32_t) (ks * p.skc) * b_lbo : a_stage + p.mt * sub_bytes;
-          // UMMAs that accumulate into the same TMEM columns serialise (each waits for the previous result), so
-          // the sub-tiles are the INNER loop: consecutive instructions hit different accumulators and pipeline.
-          if (p.folded && ks == 0) {
-            // accumulator := folded bias  (A = [255 x31, 1] in every row, B = signed base-255 digits)
-            for (int t = 0; t < p.bias_steps; t++) {
-              const uint64_t ad = a_tmpl + (a_const >> 4);
-              const uint64_t bd = b_tmpl + ((blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo) >> 4);
-              for (int j = w; j < it.mt_eff; j += kMmaWarps) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
+          if (elect_one()) {
+            // UMMAs that accumulate into the same TMEM columns serialise (each waits for the previous result), so
+            // the sub-tiles are the INNER loop: consecutive instructions hit different accumulators and pipeline.
+            if (p.folded && ks == 0) {
+              // accumulator := folded bias  (A = [255 x31, 1] in every row, B = signed base-255 digits)
+              for (int t = 0; t < p.bias_steps; t++) {
+                const uint64_t ad = a_tmpl + (a_const >> 4);
+                const uint64_t bd = b_tmpl + ((blk + (uint32_t) (p.nkc + 4 + 2 * t) * b_lbo) >> 4);
+                for (int j = w; j < it.mt_eff; j += kMmaWarps) umma_i8(d_tmem + j * p.n_mma, ad, bd, idesc_us, t != 0 ? 1u : 0u);
+              }
             }
-          }
-          for (int c = 0; c < cs; c += 2) {
-            const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
-            const uint64_t bd = b_tmpl + ((b_base + c * b_lbo) >> 4);
-            const uint64_t ad0 = a_tmpl + ((a_stage + c * kChunkBytes) >> 4);
-            const uint32_t sub16 = sub_bytes >> 4;
-            for (int j = w; j < it.mt_eff; j += kMmaWarps)
-              umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, bd, idesc_main, acc);
-            if (p.has_b2) {
-              // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
-              const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
-              const uint64_t b2 = b_tmpl + ((blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo) >> 4);
+            for (int c = 0; c < cs; c += 2) {
+              const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
+              const uint64_t bd = b_tmpl + ((b_base + c * b_lbo) >> 4);
+              const uint64_t ad0 = a_tmpl + ((a_stage + c * kChunkBytes) >> 4);
+              const uint32_t sub16 = sub_bytes >> 4;
               for (int j = w; j < it.mt_eff; j += kMmaWarps)
-                umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, b2, idesc_us, 1u);
+                umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, bd, idesc_main, acc);
+              if (p.has_b2) {
+                // + (128 - kzp) * sum_k a[m][k]: the zero-point correction as a second UMMA on the same A tile
+                const bool tail = p.k_tail_pad && (ks * p.skc + c + 2 == p.nkc);
+                const uint64_t b2 = b_tmpl + ((blk + (uint32_t) (p.nkc + (tail ? 2 : 0)) * b_lbo) >> 4);
+                for (int j = w; j < it.mt_eff; j += kMmaWarps)
+                  umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, b2, idesc_us, 1u);
+              }
             }
+            umma_commit(bar_empty + 8u * (uint32_t) stage);
+            if (ks == p.k_stages - 1) umma_commit(bar_tfull + 8u * (uint32_t) as);
           }
-          umma_commit(smem_u32(&ctl.empty[stage]));
+          __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(smem_u32(&ctl.tmem_full[as]));
       }
     }
   } else if (warp < kEpiWarps) {
@@ -870,6 +1008,39 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int lane = tid & 31;
     const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
     mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem ("ones" mode reads them)
+    if (p.out_mode == 2) {
+      // panel epilogue: one specialised loop per (requantisation form, mode), chosen once per launch
+      const uint32_t row = (uint32_t) (q * 32 + lane);
+      auto run = [&](auto rq_tag, auto folded_tag) {
+        constexpr int RQ = decltype(rq_tag)::value;
+        constexpr bool FOLDED = decltype(folded_tag)::value;
+        int as = pair - 2;
+        uint32_t as_phase = 0, k = ~0u;
+        for (long long item = first + pair * step; item < p.total_items; item += 2 * step) {
+          const Item it = decode_item(p, item);
+          k++;
+          as += 2;
+          if (as >= p.acc_stages) {
+            as -= p.acc_stages;
+            as_phase ^= 1;
+          }
+          mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
+          tc_fence_after_sync();
+          epi2_item<RQ, FOLDED>(p, it.mt_eff, tmem_base + as * p.acc_stride + ((uint32_t) (q * 32) << 16),
+                                bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4, staging, row, half,
+                                smem_u32(&ctl.tmem_empty[as]), smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1);
+          fence_proxy_async_smem();  // staging writes (generic proxy) -> tensor stores (async proxy)
+          mbar_arrive(smem_u32(&ctl.out_full[pair]));
+        }
+      };
+      using T5 = std::integral_constant<int, 5>;
+      using T6 = std::integral_constant<int, 6>;
+      if (p.folded) {
+        if (p.rq_mode == 5) run(T5{}, std::true_type{}); else run(T6{}, std::true_type{});
+      } else {
+        if (p.rq_mode == 5) run(T5{}, std::false_type{}); else run(T6{}, std::false_type{});
+      }
+    } else {
     int as = pair - 2;        // accumulator stage = (local item index) mod acc_stages, tracked without divisions
     uint32_t as_phase = 0;    // = ((local item index) / acc_stages) & 1
     uint32_t k = ~0u;         // this pair's item counter
@@ -908,10 +1079,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(smem_u32(&ctl.out_full[pair]));
       }
     }
+    }
   } else if (warp == kStoreWarp) {
     // ===================================== output stores =====================================
     const int pair = tid & 31;
-    if (pair < 2 && p.out_mode == 1) {
+    if (pair < 2 && p.out_mode == 2) {
+      // panel epilogue: every item (tails and ragged n-tiles included) leaves through 2-D tensor stores, one per panel
+      // and box of rows; the TMA unit undoes the panel swizzle and clips rows >= M / columns >= N
+      const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
+      uint32_t k = 0;
+      for (long long item = first + pair * step; item < p.total_items; item += 2 * step, k++) {
+        const Item it = decode_item(p, item);
+        mbar_wait_relaxed(smem_u32(&ctl.out_full[pair]), k & 1, 20);
+        const int rows = it.mt_eff * kTileM;
+        for (int pk = 0; pk < p.e2_panels; pk++) {
+          const int col = it.nt * p.n_tile + p.e2_col0[pk];
+          if (col >= p.goc) break;
+          const void* map = &smaps.m[p.e2_map[pk]][0];
+          for (int r0 = 0; r0 < rows; r0 += p.e2_box_rows)
+            tma_store_2d(map, staging + (uint32_t) p.e2_off[pk] + (uint32_t) (r0 * p.e2_width[pk]), col, (int) (it.m0 + r0));
+        }
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(smem_u32(&ctl.out_free[pair]));
+      }
+      bulk_wait<0>();
+    } else if (pair < 2 && p.out_mode == 1) {
       const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
       uint32_t k = 0;
       for (long long item = first + pair * step; item < p.total_items; item += 2 * step, k++) {
@@ -940,41 +1133,49 @@ __global__ void __launch_bounds__(kThreads, 1)
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
+// The dynamic-smem limit is a property of the kernel instantiation, not of a launch: it is raised ONCE to the device's
+// opt-in maximum (setting it per launch to the operator's size raced between host threads running different operators).
 template <int MODE, int VEC>
-static cudaError_t launch_one(const IgemmParams& p, const CUtensorMap& tmap, int grid, cudaStream_t stream) {
+static cudaError_t launch_one(const IgemmParams& p, const CUtensorMap& tmap, const IgemmStoreMaps& smaps, int grid,
+                              int max_smem_optin, cudaStream_t stream) {
   auto kern = q8_igemm_kernel<MODE, VEC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, p.smem_total, stream>>>(p, tmap);
+  static cudaError_t attr_status = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+  if (attr_status != cudaSuccess) return attr_status;
+  kern<<<grid, kThreads, p.smem_total, stream>>>(p, tmap, smaps);
   return cudaGetLastError();
 }
 
 // vec: 16/8/4/1 = cp.async piece size, 0 = 9-byte row runs (3x3 over 3 channels), 32 = TMA (gemm mode; `tmap` valid)
-cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, int grid, cudaStream_t stream) {
+cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, const IgemmStoreMaps* store_maps,
+                            int grid, int max_smem_optin, cudaStream_t stream) {
   alignas(64) CUtensorMap tmap;
   if (tmap_a != nullptr) {
     memcpy(&tmap, tmap_a, sizeof(tmap));
   } else {
     memset(&tmap, 0, sizeof(tmap));
   }
+  static const IgemmStoreMaps no_maps{};
+  const IgemmStoreMaps& sm = store_maps != nullptr ? *store_maps : no_maps;
+#define Q8_LAUNCH(M, V) return launch_one<M, V>(p, tmap, sm, grid, max_smem_optin, stream)
   if (mode == kModeGemm) {
     switch (vec) {
-      case 32: return launch_one<kModeGemm, 32>(p, tmap, grid, stream);
-      case 16: return launch_one<kModeGemm, 16>(p, tmap, grid, stream);
-      case 8: return launch_one<kModeGemm, 8>(p, tmap, grid, stream);
-      case 4: return launch_one<kModeGemm, 4>(p, tmap, grid, stream);
-      default: return launch_one<kModeGemm, 1>(p, tmap, grid, stream);
+      case 32: Q8_LAUNCH(kModeGemm, 32);
+      case 16: Q8_LAUNCH(kModeGemm, 16);
+      case 8: Q8_LAUNCH(kModeGemm, 8);
+      case 4: Q8_LAUNCH(kModeGemm, 4);
+      default: Q8_LAUNCH(kModeGemm, 1);
     }
   } else {
     switch (vec) {
-      case 16: return launch_one<kModeConv, 16>(p, tmap, grid, stream);
-      case 8: return launch_one<kModeConv, 8>(p, tmap, grid, stream);
-      case 4: return launch_one<kModeConv, 4>(p, tmap, grid, stream);
-      case 0: return launch_one<kModeConv, 0>(p, tmap, grid, stream);  // 9-byte row runs (3x3, 3 channels)
-      case 2: return launch_one<kModeConv, kVecRaw9>(p, tmap, grid, stream);  // ... from bulk-staged raw rows
-      default: return launch_one<kModeConv, 1>(p, tmap, grid, stream);
+      case 16: Q8_LAUNCH(kModeConv, 16);
+      case 8: Q8_LAUNCH(kModeConv, 8);
+      case 4: Q8_LAUNCH(kModeConv, 4);
+      case 0: Q8_LAUNCH(kModeConv, 0);         // 9-byte row runs (3x3, 3 channels)
+      case 2: Q8_LAUNCH(kModeConv, kVecRaw9);  // ... from bulk-staged raw rows
+      default: Q8_LAUNCH(kModeConv, 1);
     }
   }
+#undef Q8_LAUNCH
 }
 
 }  // namespace q8

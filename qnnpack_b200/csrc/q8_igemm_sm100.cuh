@@ -66,8 +66,27 @@ struct IgemmParams {
   int smem_raw_off, raw_cap, raw_bufs;  // raw-row staging (3x3x3 stem loader): raw_bufs (2..4) buffers of raw_cap bytes
   int raw_batch;              // images in the input tensor (bounds the bulk copies)
 
+  // out_mode 2 ("panel" epilogue): the pair's staging image is a set of column panels [panel][sub-tile*128 + row][width],
+  // width in {128, 64, 32, 16} bytes with the matching TMA swizzle (conflict-free 16-byte staging stores for every
+  // pitch), written to global memory by 2-D tensor stores that clip rows >= M and columns >= N themselves.
+  int e2_panels;              // panels per n-tile (greedy split of n_tile into 128/64/32/16)
+  int e2_box_rows;            // rows per tensor store: 256 when mt is even, else 128
+  int e2_col0[4];             // first column of panel k inside the n-tile
+  int e2_width[4];            // its width in bytes
+  int e2_off[4];              // its byte offset inside the pair's staging buffer (1024-aligned)
+  int e2_map[4];              // which tensor map (width class: 0 = 16, 1 = 32, 2 = 64, 3 = 128)
+  // per epilogue unit c of a sub-tile (W = 32 columns folded / 16 otherwise):
+  //   x = byte offset of the unit's first 16-byte chunk relative to the staging buffer, for row 0 of sub-tile 0
+  //   y = pitch | lsh << 8 | mask << 16   (swizzle: chunk bits ^= (row << lsh) & mask)
+  uint2 e2_unit[16];
+
   int izp, kzp;
   Q8Requant rq;
+};
+
+// tensor maps of the output for the panel epilogue, one per panel-width class
+struct IgemmStoreMaps {
+  alignas(64) unsigned char m[4][128];
 };
 
 }  // namespace q8

@@ -31,7 +31,9 @@
 #include "requant_dev.cuh"
 
 namespace q8 {
-cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, int grid, cudaStream_t stream);
+cudaError_t measure_int8_peak(int num_sms, int iters, int reps, cudaStream_t stream, double* tops, double* ms_out);
+cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, const IgemmStoreMaps* store_maps,
+                            int grid, int max_smem_optin, cudaStream_t stream);
 }
 
 #define QNNP_EXPORT extern "C" __attribute__((visibility("default")))
@@ -138,6 +140,22 @@ bool make_tmap_a(CUtensorMap* tm, const uint8_t* in, size_t M, size_t in_stride,
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Output matrix [M][out_stride] (first N bytes of a row used) as a 2-D tensor {N, M} for the panel epilogue's stores:
+// box = {width, rows}, shared-memory side swizzled to match the panel (width 128 / 64 / 32 bytes; 16: none).
+bool make_tmap_out(void* tm, uint8_t* out, size_t M, size_t N, size_t out_stride, int width, int rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t) N, (cuuint64_t) M};
+  const cuuint64_t gstride[1] = {(cuuint64_t) out_stride};
+  const cuuint32_t box[2] = {(cuuint32_t) width, (cuuint32_t) rows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUtensorMapSwizzle sw = width == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : width == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                           : width == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return fn((CUtensorMap*) tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, out, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
@@ -305,6 +323,9 @@ enum KernelKind { kKindNone = 0, kKindIgemmGemm, kKindIgemmConv, kKindDw3x3, kKi
 // ------------------------------------------------------------------------------------------------
 // operator object (opaque to users; reference src/qnnpack/operator.h:39-102)
 // ------------------------------------------------------------------------------------------------
+struct qnnp_launch_plan;
+void delete_plan(qnnp_launch_plan* p);
+
 struct qnnp_operator {
   KernelKind kind = kKindNone;
   bool is_fc = false;
@@ -343,6 +364,7 @@ struct qnnp_operator {
   uint8_t* output = nullptr;
   size_t in_stride = 0, out_stride = 0;
   bool in_on_device = false, out_on_device = false;
+  struct qnnp_launch_plan* plan = nullptr;  // cached launch state (built in setup / first run; see build_plan)
   // staging for host pointers
   uint8_t* d_in = nullptr;
   uint8_t* d_out = nullptr;
@@ -361,6 +383,7 @@ void free_operator(qnnp_operator* op) {
   cudaFree(op->d_dwtc_bias);
   cudaFree(op->d_in);
   cudaFree(op->d_out);
+  delete_plan(op->plan);
   delete op;
 }
 
@@ -458,11 +481,13 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
   Cand best{0, 0, 0, 0, 0, 0, -1, false, 1e30};
   const int skc_min = pl->nkc < 4 ? pl->nkc : 4;
   for (int mt = mt_max; mt >= 1; mt--) {
-    const int staging = pl->bulk_capable ? mt * q8::kTileM * (int) goc : 0;  // per epilogue pair
+    // per epilogue pair: the output tile of an item as column panels of n_tile bytes per row in total (panel epilogue),
+    // which also covers the dense goc-pitch image of the 1-D bulk path (goc <= n_tile when there is one n-tile)
+    const int staging = mt * q8::kTileM * pl->n_tile;
     for (int skc = pl->nkc; skc >= 2; skc -= 2) {
       if (skc > 16 && skc != pl->nkc && (skc % 8) != 0) continue;  // prune the search
       const int a_stage = mt * skc * q8::kChunkBytes;
-      const long long fixed = pl->bias_bytes + aconst_bytes + 2LL * staging;
+      const long long fixed = pl->bias_bytes + aconst_bytes + 2LL * staging + 1024;  // (+ alignment of the staging base)
       const int resident = ((long long) pl->w_total + fixed + 3LL * a_stage <= smem_max) ? 1 : 0;
       if (folded && !resident) continue;
       const int stage_bytes = a_stage + (resident ? 0 : skc * pl->n_mma * 16);
@@ -491,7 +516,7 @@ bool plan_igemm(size_t K, size_t goc, uint32_t groups, int smem_optin, int folde
   pl->smem_bias_off = (int) round_up(pl->b_resident ? pl->w_total : 0, 128);
   pl->smem_aconst_off = pl->smem_bias_off + pl->bias_bytes;
   pl->smem_a_off = pl->smem_aconst_off + aconst_bytes;
-  pl->smem_stage_off = pl->smem_a_off + pl->num_stages * pl->stage_bytes;
+  pl->smem_stage_off = (int) round_up(pl->smem_a_off + pl->num_stages * pl->stage_bytes, 1024);  // swizzle atoms: 1024 B
   pl->smem_total = pl->smem_stage_off + 2 * pl->staging_bytes + 1024;
   return true;
 }
@@ -743,11 +768,83 @@ enum qnnp_status pack_direct(qnnp_operator* op, const uint8_t* kernel, const int
 }
 
 // ------------------------------------------------------------------------------------------------
-// launch
+// launch plans
 // ------------------------------------------------------------------------------------------------
-enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cudaStream_t stream) {
+// Everything a launch needs besides the stream — kernel parameters, tensor maps, grid, loader / store variants, the
+// depthwise tiling — is a function of the operator and of the (input, output) pointers it was set up with.  It is
+// computed ONCE, in qnnp_setup_* when both pointers are device pointers (else at the first run, when the staging
+// buffers exist), and cached in the operator: qnnp_run_operator only launches.  Environment switches are read while
+// the plan is built, never on the launch path.  (Round 1 redid all of it, ~10 getenv() calls and a tensor-map encode
+// included, on every run: SURVEY.md §3.4 puts this work in setup, like the reference's indirection-buffer setup,
+// src/convolution.c:428-492.)
+enum PlanPath { kPlanNone = 0, kPlanIgemm, kPlanDwUmma, kPlanDwStream, kPlanDwGeneric, kPlanDirect };
+
+bool env_set(const char* name) { return getenv(name) != nullptr; }
+
+// Panel epilogue tables (q8_igemm_sm100.cuh: out_mode 2): n_tile is split greedily into panels of 128/64/32/16 bytes.
+void fill_panel_tables(q8::IgemmParams& p) {
+  const int W = p.folded ? 32 : 16;
+  int col = 0, off = 0, k = 0;
+  const int widths[4] = {128, 64, 32, 16};
+  for (int wi = 0; wi < 4; wi++) {
+    const int w = widths[wi];
+    while (p.n_tile - col >= w && k < 4) {
+      p.e2_col0[k] = col, p.e2_width[k] = w, p.e2_off[k] = off, p.e2_map[k] = 3 - wi;
+      off += w * q8::kTileM * p.mt;
+      col += w;
+      k++;
+    }
+  }
+  p.e2_panels = k;
+  p.e2_box_rows = (p.mt % 2 == 0) ? 256 : 128;
+  const int per_sub = (p.n_tile + W - 1) / W;
+  for (int c = 0; c < per_sub && c < 16; c++) {
+    const int ucol = c * W;
+    int pk = 0;
+    while (pk + 1 < k && ucol >= p.e2_col0[pk] + p.e2_width[pk]) pk++;
+    const int w = p.e2_width[pk];
+    const uint32_t lsh = w == 128 ? 4 : (w == 64 ? 3 : (w == 32 ? 2 : 0));
+    const uint32_t mask = w == 128 ? 0x70 : (w == 64 ? 0x30 : (w == 32 ? 0x10 : 0));
+    p.e2_unit[c].x = (uint32_t) (p.e2_off[pk] + (ucol - p.e2_col0[pk]));
+    p.e2_unit[c].y = (uint32_t) w | (lsh << 8) | (mask << 16);
+  }
+}
+
+}  // namespace
+
+struct qnnp_launch_plan {
+  bool valid = false;
+  PlanPath path = kPlanNone;
+  const uint8_t* in = nullptr;
+  uint8_t* out = nullptr;
+  int grid = 0;
+  // igemm
+  q8::IgemmParams ig{};
+  int ig_mode = 0, ig_vec = 0;
+  bool has_tmap_a = false, has_smaps = false;
+  alignas(64) CUtensorMap tmap_a;
+  q8::IgemmStoreMaps smaps;
+  // depthwise
+  q8::DwTcParams tp{};
+  alignas(64) CUtensorMap dw_tmap;
+  q8::DwStreamParams sp{};
+  q8::DwParams dp{};
+  int dw_cv = 1;
+  // direct
+  q8::DirectParams dir{};
+};
+
+void delete_plan(qnnp_launch_plan* p) { delete p; }
+
+namespace {
+
+enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, uint8_t* out) {
+  if (op->plan == nullptr) op->plan = new (std::nothrow) qnnp_launch_plan();
+  if (op->plan == nullptr) return qnnp_status_out_of_memory;
+  qnnp_launch_plan& pl = *op->plan;
+  pl.valid = false;
+  pl.in = in, pl.out = out;
   const size_t M = op->batch * op->out_h * op->out_w;
-  cudaError_t e = cudaSuccess;
   switch (op->kind) {
     case kKindIgemmGemm:
     case kKindIgemmConv: {
@@ -789,10 +886,28 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
       p.rq_mode = op->rq_mode;
-      // output path
+      // output path: 2 = swizzled panels + 2-D tensor stores (any item, any N, pixel-stride gaps); 1 = dense image + one
+      // 1-D bulk store per full item; 0 = per-thread global stores
       const bool bulk = op->bulk_capable && op->out_stride == op->goc && ((uintptr_t) out % 16) == 0 &&
-          getenv("QNNP_CUDA_NO_BULK_STORE") == nullptr;
+          !env_set("QNNP_CUDA_NO_BULK_STORE");
       p.out_mode = bulk ? 1 : 0;
+      pl.has_smaps = false;
+      if ((op->rq_mode == 5 || op->rq_mode == 6) && op->groups == 1 && ((uintptr_t) out % 16) == 0 && (op->out_stride % 16) == 0 &&
+          g_lib.dbg_acc == nullptr && !env_set("QNNP_CUDA_NO_PANEL_STORE")) {
+        fill_panel_tables(p);
+        bool ok = true;
+        bool done[4] = {false, false, false, false};
+        for (int k = 0; k < p.e2_panels && ok; k++) {
+          const int cls = p.e2_map[k];
+          if (done[cls]) continue;
+          done[cls] = true;
+          ok = make_tmap_out(&pl.smaps.m[cls][0], out, M, op->goc, op->out_stride, p.e2_width[k], p.e2_box_rows);
+        }
+        if (ok) {
+          p.out_mode = 2;
+          pl.has_smaps = true;
+        }
+      }
       int ov = pow2_align((uintptr_t) out, 32);
       ov = pow2_align((uintptr_t) op->out_stride, ov);
       if (op->groups > 1) ov = pow2_align((uintptr_t) op->goc, ov);  // group offset g*goc (tile offsets are multiples of 16)
@@ -807,12 +922,12 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       // 3x3 over 3 dense channels (MobileNetV2 stem): the taps of a kernel row are one 9-byte run
       if (mode == q8::kModeConv && vec == 1 && op->kh == 3 && op->kw == 3 && op->gic == 3 && op->dil_w == 1 &&
           op->in_stride == 3 && op->k_stages == 1 && op->in_w >= 3 && ((uintptr_t) in % 4) == 0 &&
-          (M * 0 + op->batch * op->in_h * op->in_w * 3) % 4 == 0 && getenv("QNNP_CUDA_NO_RUN9") == nullptr)
+          (op->batch * op->in_h * op->in_w * 3) % 4 == 0 && !env_set("QNNP_CUDA_NO_RUN9"))
         vec = 0;
       // ... and those runs are read from bulk-staged raw input rows when the tensor can be bulk-copied (16-byte aligned
       // base and size) and an item never spans more than two images; the A ring gives up stages for the two raw buffers
       if (vec == 0 && ((uintptr_t) in % 16) == 0 && ((size_t) op->batch * op->in_h * op->in_w * 3) % 16 == 0 &&
-          (size_t) op->out_h * op->out_w >= (size_t) op->mt * q8::kTileM && getenv("QNNP_CUDA_NO_RAW9") == nullptr) {
+          (size_t) op->out_h * op->out_w >= (size_t) op->mt * q8::kTileM && !env_set("QNNP_CUDA_NO_RAW9")) {
         const int rows_out = (int) ((op->mt * q8::kTileM + op->out_w - 2) / op->out_w) + 1;
         const int rows_in = (rows_out + 1) * (int) op->stride_h + 2 * (int) ((op->kh - 1) * op->dil_h + 1);
         const int raw_cap = (int) round_up((size_t) rows_in * op->in_w * 3 + 64, 128);
@@ -820,12 +935,12 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         int max_bufs = 4;
         if (const char* ev = getenv("QNNP_CUDA_RAW_BUFS")) max_bufs = atoi(ev) < 2 ? 2 : (atoi(ev) > 4 ? 4 : atoi(ev));
         for (int bufs = max_bufs; bufs >= 2 && vec == 0; bufs--) {
-          const int fixed = p.smem_a_off + 2 * p.staging_bytes + 1024 + bufs * raw_cap;
+          const int fixed = p.smem_a_off + 2 * p.staging_bytes + 2048 + bufs * raw_cap;
           int stages = p.num_stages;
           while (stages > 3 && fixed + stages * p.stage_bytes > g_lib.max_smem_optin - kCtlReserve) stages--;
           if (fixed + stages * p.stage_bytes > g_lib.max_smem_optin - kCtlReserve) continue;
           p.num_stages = stages;
-          p.smem_stage_off = p.smem_a_off + stages * p.stage_bytes;
+          p.smem_stage_off = (int) round_up(p.smem_a_off + stages * p.stage_bytes, 1024);
           p.smem_raw_off = p.smem_stage_off + 2 * p.staging_bytes;
           p.raw_cap = raw_cap;
           p.raw_bufs = bufs;
@@ -835,50 +950,38 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         }
       }
       // 1x1 / FC with 16-byte aligned rows: the TMA loads the activation tiles
-      alignas(64) CUtensorMap tmap;
-      const void* tmap_ptr = nullptr;
+      pl.has_tmap_a = false;
       if (mode == q8::kModeGemm && vec == 16 && op->groups == 1 && (op->K % 16) == 0 && op->skc <= 256 && M < (1ull << 31) &&
-          getenv("QNNP_CUDA_NO_TMA") == nullptr && make_tmap_a(&tmap, in, M, op->in_stride, op->K, op->skc)) {
+          !env_set("QNNP_CUDA_NO_TMA") && make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K, op->skc)) {
         vec = 32;
-        tmap_ptr = &tmap;
+        pl.has_tmap_a = true;
       }
-      const long long grid = persistent_grid(p.total_items);
-      e = q8::launch_q8_igemm(p, mode, vec, tmap_ptr, (int) grid, stream);
+      pl.grid = (int) persistent_grid(p.total_items);
+      pl.ig = p;
+      pl.ig_mode = mode, pl.ig_vec = vec;
+      pl.path = kPlanIgemm;
       break;
     }
     case kKindDw3x3: {
-      q8::DwParams p{};
-      p.in = in, p.out = out;
-      p.w32 = (const int32_t*) op->d_weights;
-      p.bias = op->d_bias;
-      p.in_stride = (long long) op->in_stride, p.out_stride = (long long) op->out_stride;
-      p.batch = (int) op->batch, p.channels = (int) op->groups, p.c_pad = op->c_pad;
-      p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
-      p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w, p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w;
-      p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
-      p.izp = op->izp;
-      p.rq = op->rq, p.rq_mode = op->rq_mode;
       int cv = pow2_align((uintptr_t) in, 4);
       cv = pow2_align((uintptr_t) out, cv);
       cv = pow2_align((uintptr_t) op->in_stride, cv);
       cv = pow2_align((uintptr_t) op->out_stride, cv);
       cv = pow2_align((uintptr_t) op->groups, cv);
       const bool stream_ok = cv == 4 && op->dil_h == 1 && op->dil_w == 1 && op->stride_h == op->stride_w &&
-          (op->stride_h == 1 || op->stride_h == 2) && getenv("QNNP_CUDA_DW_GENERIC") == nullptr;
+          (op->stride_h == 1 || op->stride_h == 2) && !env_set("QNNP_CUDA_DW_GENERIC");
       // tensor-core path: channels % 16 == 0 and 16-byte aligned pixels (TMA boxes, 16-byte output stores)
-      q8::DwTcParams tp;
-      alignas(64) CUtensorMap dw_tmap;
       // (measured on MobileNetV2 at batch 4096: the tcgen05 kernel wins everywhere except stride-2 layers tiled by rows,
       // where one channel group per item fits and the CUDA-core streaming kernel is ~8% faster; QNNP_CUDA_DW_UMMA=1
       // forces the tensor-core path for every eligible shape, QNNP_CUDA_DW_NO_UMMA=1 disables it)
-      const bool force_tc = getenv("QNNP_CUDA_DW_UMMA") != nullptr;
-      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32 && getenv("QNNP_CUDA_DW_S2_UMMA") == nullptr;
-      const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && getenv("QNNP_CUDA_DW_NO_UMMA") == nullptr &&
-          (force_tc || !s2_rows) &&
+      const bool force_tc = env_set("QNNP_CUDA_DW_UMMA");
+      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32 && !env_set("QNNP_CUDA_DW_S2_UMMA");
+      q8::DwTcParams& tp = pl.tp;
+      const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && !env_set("QNNP_CUDA_DW_NO_UMMA") && (force_tc || !s2_rows) &&
           ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
           plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
                        (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dw_wmode, g_lib.max_smem_optin, &tp) &&
-          make_tmap_dw(&dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
+          make_tmap_dw(&pl.dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
                        tp.box_rows, tp.nb);
       if (tc_ok) {
         tp.out = out, tp.wpack = op->d_dwtc_w, tp.bias_cls = op->d_dwtc_bias;
@@ -896,8 +999,8 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
           tp.inv_g = (65536u + (uint32_t) tp.mt - 1) / (uint32_t) tp.mt;
           tp.inv_tail = (65536u + (uint32_t) tail - 1) / (uint32_t) tail;
         }
-        e = q8::launch_q8_dwconv3x3_umma(tp, &dw_tmap, (int) grid, stream);
-        if (e == cudaSuccess) g_lib.dw_umma_launches.fetch_add(1);
+        pl.grid = (int) grid;
+        pl.path = kPlanDwUmma;
       } else if (stream_ok) {
         q8::DwStreamParams sp{};
         sp.in = in, sp.out = out;
@@ -908,9 +1011,23 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
         sp.stride = (int) op->stride_h, sp.pad_top = (int) op->pad_top, sp.pad_left = (int) op->pad_left;
         sp.wmode = op->dw_wmode, sp.izp = op->izp;
         sp.rq = op->rq, sp.rq_mode = op->rq_mode, sp.shift_mul = q8::requant_shift_mul(op->rq);
-        e = q8::launch_q8_dwconv3x3_stream(sp, stream);
+        pl.sp = sp;
+        pl.path = kPlanDwStream;
       } else {
-        e = q8::launch_q8_dwconv3x3(p, cv == 4 ? 4 : 1, stream);
+        q8::DwParams p{};
+        p.in = in, p.out = out;
+        p.w32 = (const int32_t*) op->d_weights;
+        p.bias = op->d_bias;
+        p.in_stride = (long long) op->in_stride, p.out_stride = (long long) op->out_stride;
+        p.batch = (int) op->batch, p.channels = (int) op->groups, p.c_pad = op->c_pad;
+        p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
+        p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w, p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w;
+        p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
+        p.izp = op->izp;
+        p.rq = op->rq, p.rq_mode = op->rq_mode;
+        pl.dp = p;
+        pl.dw_cv = cv == 4 ? 4 : 1;
+        pl.path = kPlanDwGeneric;
       }
       break;
     }
@@ -928,11 +1045,37 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
       p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
-      e = q8::launch_q8_direct_conv(p, stream);
+      pl.dir = p;
+      pl.path = kPlanDirect;
       break;
     }
     default:
       return qnnp_status_invalid_parameter;
+  }
+  pl.valid = true;
+  return qnnp_status_success;
+}
+
+enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cudaStream_t stream) {
+  if (op->plan == nullptr || !op->plan->valid || op->plan->in != in || op->plan->out != out) {
+    const enum qnnp_status st = build_plan(op, in, out);
+    if (st != qnnp_status_success) return st;
+  }
+  const qnnp_launch_plan& pl = *op->plan;
+  cudaError_t e = cudaSuccess;
+  switch (pl.path) {
+    case kPlanIgemm:
+      e = q8::launch_q8_igemm(pl.ig, pl.ig_mode, pl.ig_vec, pl.has_tmap_a ? &pl.tmap_a : nullptr,
+                              pl.has_smaps ? &pl.smaps : nullptr, pl.grid, g_lib.max_smem_optin, stream);
+      break;
+    case kPlanDwUmma:
+      e = q8::launch_q8_dwconv3x3_umma(pl.tp, &pl.dw_tmap, pl.grid, g_lib.max_smem_optin, stream);
+      if (e == cudaSuccess) g_lib.dw_umma_launches.fetch_add(1);
+      break;
+    case kPlanDwStream: e = q8::launch_q8_dwconv3x3_stream(pl.sp, stream); break;
+    case kPlanDwGeneric: e = q8::launch_q8_dwconv3x3(pl.dp, pl.dw_cv, stream); break;
+    case kPlanDirect: e = q8::launch_q8_direct_conv(pl.dir, stream); break;
+    default: return qnnp_status_invalid_parameter;
   }
   g_lib.launches.fetch_add(1);
   return map_cuda(e, "kernel launch");
@@ -992,6 +1135,19 @@ enum qnnp_status run_impl(qnnp_operator* op, bool async) {
       return st;
   }
   return map_cuda(cudaStreamSynchronize(stream), "stream synchronize");
+}
+
+// Common tail of qnnp_setup_*: classify the pointers and, when the operator can run zero-copy, build its launch plan now
+// (tensor maps, tiling, kernel variant) so that qnnp_run_operator only launches.
+enum qnnp_status finish_setup(qnnp_operator* op) {
+  op->in_on_device = is_device_pointer(op->input);
+  op->out_on_device = is_device_pointer(op->output);
+  if (op->plan != nullptr) op->plan->valid = false;
+  if (op->in_on_device && op->out_on_device) {
+    bind_device();
+    return build_plan(op, op->input, op->output);
+  }
+  return qnnp_status_success;
 }
 
 size_t output_dimension(size_t padded_input, size_t kernel, size_t dilation, size_t subsampling) {
@@ -1107,6 +1263,7 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_convolution2d_nhwc_q8(
   if (op == nullptr) return qnnp_status_invalid_parameter;
   if (batch_size == 0) {  // src/convolution.c:396-399
     op->batch = 0;
+    if (op->plan != nullptr) op->plan->valid = false;
     return qnnp_status_success;
   }
   if (input_width == 0 || input_height == 0) {
@@ -1119,9 +1276,7 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_convolution2d_nhwc_q8(
   op->out_h = output_dimension(op->pad_top + input_height + op->pad_bottom, op->kh, op->dil_h, op->stride_h);
   op->out_w = output_dimension(op->pad_left + input_width + op->pad_right, op->kw, op->dil_w, op->stride_w);
   op->output = output, op->out_stride = output_stride;
-  op->in_on_device = is_device_pointer(input);
-  op->out_on_device = is_device_pointer(output);
-  return qnnp_status_success;
+  return finish_setup(op);
 }
 
 QNNP_EXPORT enum qnnp_status qnnp_create_fully_connected_nc_q8(
@@ -1172,6 +1327,7 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_fully_connected_nc_q8(
   if (op == nullptr) return qnnp_status_invalid_parameter;
   if (batch_size == 0) {
     op->batch = 0;
+    if (op->plan != nullptr) op->plan->valid = false;
     return qnnp_status_success;
   }
   // src/fully-connected.c:149-158: one "image" of batch_size x 1 pixels
@@ -1179,9 +1335,7 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_fully_connected_nc_q8(
   op->in_h = batch_size, op->in_w = 1, op->out_h = batch_size, op->out_w = 1;
   op->input = input, op->in_stride = input_stride;
   op->output = output, op->out_stride = output_stride;
-  op->in_on_device = is_device_pointer(input);
-  op->out_on_device = is_device_pointer(output);
-  return qnnp_status_success;
+  return finish_setup(op);
 }
 
 QNNP_EXPORT enum qnnp_status qnnp_run_operator(qnnp_operator_t op, pthreadpool_t threadpool) {
@@ -1216,6 +1370,16 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_operator_packed_bias(qnnp_operator_t op, 
   *size_bytes = op->bias_count * sizeof(int32_t);
   return qnnp_status_success;
 }
+/* Measured dense int8 tensor-core peak (tera-ops/s) of this device: smem-resident tcgen05.mma kind::i8 loop,
+ * `reps` timed launches of `iters` x 8 UMMAs per SM (q8_peak_sm100.cu). */
+QNNP_EXPORT enum qnnp_status qnnp_cuda_measure_int8_peak(int iters, int reps, double* tops, double* ms_per_launch) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (iters <= 0 || reps <= 0 || tops == nullptr || ms_per_launch == nullptr) return qnnp_status_invalid_parameter;
+  bind_device();
+  const cudaError_t e = q8::measure_int8_peak(g_lib.num_sms, iters, reps, g_lib.stream, tops, ms_per_launch);
+  if (e == cudaSuccess) g_lib.launches.fetch_add((unsigned long long) reps + 1);
+  return map_cuda(e, "qnnp_cuda_measure_int8_peak");
+}
 QNNP_EXPORT unsigned long long qnnp_cuda_launch_count(void) { return g_lib.launches.load(); }
 QNNP_EXPORT unsigned long long qnnp_cuda_debug_dw_umma_launch_count(void) { return g_lib.dw_umma_launches.load(); }
 QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, int folded, int bias_steps, int out[24]) {
@@ -1228,6 +1392,17 @@ QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, 
                      pl.blk_chunks, pl.good};
   for (int i = 0; i < 24; i++) out[i] = v[i];
   return 1;
+}
+/* Panel-epilogue tables for an n-tile of `n_tile` columns, `mt` sub-tiles per item (CPU-callable; tests/test_planner.py
+ * replays the staging writes and the swizzled tensor-store reads on them).  out: [0] panels, [1] box_rows,
+ * [2+4k..] col0, width, off, map of panel k (4 panels), [18+2c..] x, y of unit c (16 units). */
+QNNP_EXPORT void qnnp_cuda_debug_panel_tables(int n_tile, int mt, int folded, int out[50]) {
+  q8::IgemmParams p{};
+  p.n_tile = n_tile, p.mt = mt, p.folded = folded;
+  fill_panel_tables(p);
+  out[0] = p.e2_panels, out[1] = p.e2_box_rows;
+  for (int k = 0; k < 4; k++) out[2 + 4 * k] = p.e2_col0[k], out[3 + 4 * k] = p.e2_width[k], out[4 + 4 * k] = p.e2_off[k], out[5 + 4 * k] = p.e2_map[k];
+  for (int c = 0; c < 16; c++) out[18 + 2 * c] = (int) p.e2_unit[c].x, out[19 + 2 * c] = (int) p.e2_unit[c].y;
 }
 /* Depthwise tensor-core tiling for a geometry (CPU-callable): fills out[40], returns 0 when the shape is not eligible. */
 QNNP_EXPORT int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, int in_w, int out_h, int out_w, int stride,

@@ -65,6 +65,14 @@ class Layer:
         return (batch * self.h * self.h * self.cin + self.cout * (self.k_eff + 4)
                 + batch * self.out_h * self.out_h * self.cout)
 
+    @property
+    def in_elems_per_image(self):
+        return self.cin if self.kind == "fc" else self.h * self.h * self.cin
+
+    @property
+    def out_elems_per_image(self):
+        return self.cout if self.kind == "fc" else self.out_h * self.out_h * self.cout
+
 
 def layers() -> list[Layer]:
     seq = [Layer("stem", "conv", 224, 3, 32, 3, 2)]
@@ -103,6 +111,17 @@ def requant_scale(layer: Layer) -> float:
     return float(np.float32(1.0 / (128.0 * math.sqrt(layer.k_eff))))
 
 
+def layer_kwargs(layer: Layer):
+    """create-kwargs (geometry + quantisation) of a layer for qnnpack_b200.api.QnnpackLibrary."""
+    q = dict(izp=127, input_scale=1.0, kzp=127, kernel_scale=requant_scale(layer), ozp=127, output_scale=1.0,
+             qmin=0, qmax=255)
+    if layer.kind == "fc":
+        return q
+    p = layer.pad
+    return dict(pad=(p, p, p, p), ksize=(layer.k, layer.k), stride=(layer.stride, layer.stride),
+                dilation=(1, 1), groups=layer.groups, gic=layer.gic, goc=layer.goc, **q)
+
+
 def layer_params(layer: Layer, seed: int):
     """-> (kernel uint8, bias int32, create-kwargs) for qnnpack_b200.api.QnnpackLibrary."""
     rng = np.random.default_rng(seed)
@@ -111,13 +130,29 @@ def layer_params(layer: Layer, seed: int):
     else:
         kernel = rng.integers(0, 256, (layer.groups, layer.goc, layer.k, layer.k, layer.gic), dtype=np.uint8)
     bias = rng.integers(-10000, 10001, (layer.cout,), dtype=np.int32)
-    q = dict(izp=127, input_scale=1.0, kzp=127, kernel_scale=requant_scale(layer), ozp=127, output_scale=1.0,
-             qmin=0, qmax=255)
+    return kernel, bias, layer_kwargs(layer)
+
+
+def create_node(lib, layer: Layer, kernel, bias):
+    """One operator of the stack in any qnnpack.h implementation (product or reference)."""
+    kw = layer_kwargs(layer)
     if layer.kind == "fc":
-        return kernel, bias, q
-    p = layer.pad
-    return kernel, bias, dict(pad=(p, p, p, p), ksize=(layer.k, layer.k), stride=(layer.stride, layer.stride),
-                              dilation=(1, 1), groups=layer.groups, gic=layer.gic, goc=layer.goc, **q)
+        st, op = lib.create_fully_connected(kernel, bias, **kw)
+    else:
+        st, op = lib.create_convolution(kernel, bias, **kw)
+    if st != 0:
+        raise RuntimeError(f"create {layer.name} -> status {st}")
+    return op
+
+
+def setup_node(lib, layer: Layer, op, batch, inputs, out):
+    """inputs: [buffer] (NumPy array or device address); batch = images (rows for the classifier)."""
+    if layer.kind == "fc":
+        st = lib.setup_fully_connected(op, batch, inputs[0], layer.cin, out, layer.cout)
+    else:
+        st = lib.setup_convolution(op, batch, layer.h, layer.h, inputs[0], layer.cin, out, layer.cout)
+    if st != 0:
+        raise RuntimeError(f"setup {layer.name} -> status {st}")
 
 
 def make_params(seed: int = 0, zero: bool = False, only=None):
@@ -139,16 +174,11 @@ class Stack:
         self.layers = layers() if only is None else only
         self.ops = []
         for i, l in enumerate(self.layers):
-            kernel, bias, kw = layer_params(l, seed * 1000 + i)
             if params is not None:  # e.g. received from rank 0
                 kernel, bias = params[i]
-            if l.kind == "fc":
-                st, op = lib.create_fully_connected(kernel, bias, **kw)
             else:
-                st, op = lib.create_convolution(kernel, bias, **kw)
-            if st != 0:
-                raise RuntimeError(f"create {l.name} -> status {st}")
-            self.ops.append(op)
+                kernel, bias, _ = layer_params(l, seed * 1000 + i)
+            self.ops.append(create_node(lib, l, kernel, bias))
 
     def max_activation_bytes(self, batch):
         m = 0

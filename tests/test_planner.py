@@ -68,3 +68,57 @@ def test_grouped_plan(plan):
     for groups in (2, 3, 8):
         d = plan(40, 24, groups, 0, 0)
         check(d, 40, 24, 0)
+
+
+# ---- panel epilogue (q8_igemm_sm100.cu, out_mode 2): staging writes replayed against the TMA swizzle definition ----
+def _tma_swizzle(addr, width):  # noqa: E302
+    """Shared-memory byte address -> physical address for a box whose inner extent equals the swizzle span: the 16-byte
+    chunk bits [4, 4+b) are XORed with address bits [7, 7+b)  (SWIZZLE_128B b=3, 64B b=2, 32B b=1, none b=0)."""
+    b = {128: 3, 64: 2, 32: 1, 16: 0}[width]
+    return addr ^ (((addr >> 7) & ((1 << b) - 1)) << 4)
+
+
+@pytest.mark.parametrize("folded", [0, 1])
+@pytest.mark.parametrize("n_tile,mt", [(16, 8), (32, 8), (48, 5), (64, 4), (96, 2), (112, 2), (144, 1), (160, 1), (192, 1),
+                                       (240, 1), (256, 1), (128, 2), (80, 3)])
+def test_panel_epilogue_tables(n_tile, mt, folded):
+    import numpy as np
+    from qnnpack_b200 import build
+    lib = C.CDLL(build.build())
+    out = (C.c_int * 50)()
+    lib.qnnp_cuda_debug_panel_tables(n_tile, mt, folded, out)
+    panels, box_rows = out[0], out[1]
+    pan = [(out[2 + 4 * k], out[3 + 4 * k], out[4 + 4 * k], out[5 + 4 * k]) for k in range(panels)]
+    assert sum(w for _, w, _, _ in pan) == n_tile and box_rows == (256 if mt % 2 == 0 else 128)
+    W = 32 if folded else 16
+    per_sub = (n_tile + W - 1) // W
+    rows = mt * 128
+    staging = np.full(rows * n_tile, -1, np.int64)           # value = row * 1000 + column
+    phase_slots = {}
+    for j in range(mt):
+        for c in range(per_sub):
+            x, y = out[18 + 2 * c], out[19 + 2 * c]
+            pitch, lsh, mask = y & 0xFF, (y >> 8) & 0xFF, y >> 16
+            width = min(W, n_tile - c * W)
+            for row in range(128):
+                jrow = j * 128 + row
+                a0 = (x + jrow * pitch) ^ ((row << lsh) & mask)
+                for h in range(width // 16):
+                    a = a0 ^ (16 * h)
+                    col = c * W + 16 * h
+                    assert (staging[a:a + 16] == -1).all(), "two chunks land on the same bytes"
+                    staging[a:a + 16] = jrow * 1000 + col + np.arange(16)
+                    phase_slots.setdefault((j, c, h, row // 8), set()).add((a >> 4) & 7)
+    assert (staging >= 0).all()
+    # every 8-lane store phase (8 consecutive rows, same chunk) hits 8 different 16-byte bank groups
+    assert all(len(v) == 8 for v in phase_slots.values())
+    # the tensor stores read each panel through the hardware swizzle and must see row-major [row][column]
+    for col0, width, off, cls in pan:
+        assert off % 1024 == 0 and cls == {16: 0, 32: 1, 64: 2, 128: 3}[width]
+        for r0 in range(0, rows, box_rows):
+            for r in range(min(box_rows, rows - r0)):
+                for cc in range(0, width, 16):
+                    logical = off + (r0 + r) * width + cc          # dense box image relative to the box start ...
+                    phys = off + r0 * width + _tma_swizzle(r * width + cc, width)  # ... as the TMA addresses it
+                    assert (staging[phys:phys + 16] == (r0 + r) * 1000 + col0 + cc + np.arange(16)).all(), (col0, r0 + r, cc)
+                    del logical
