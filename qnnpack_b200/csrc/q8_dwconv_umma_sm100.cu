@@ -172,7 +172,12 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
       int32_t y[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        y[i] = q8_requant_u_unclamped((uint32_t) n[i], p.rq.u_m2, p.rq.u_k2, p.rq.u_sm);
+        // the final arithmetic shift alternates between the FMA pipe (IMAD.HI, 4 cycles per warp on the half-rate
+        // "heavy" pipe that IMAD.HI.U32 above already loads) and the ALU pipe (SHF, 2 cycles): see q8_igemm_sm100.cu
+        const uint32_t nu = (uint32_t) n[i];
+        const uint32_t hi = (uint32_t) (((uint64_t) nu * p.rq.u_m2 + p.rq.u_k2) >> 32);
+        const int32_t tt = (int32_t) (hi + (nu >> 31));
+        y[i] = (i & 1) ? (tt >> p.rq.shift) : __mulhi(tt, p.rq.u_sm);
         if constexpr (RQ == 6) y[i] = min(max(y[i], p.rq.qmin), p.rq.qmax);
       }
       o[t] = pack_sat_u8x4(y[0], y[1], y[2], y[3]);
@@ -311,30 +316,40 @@ __global__ void __launch_bounds__(kThreads, 1)
     mma_role<NB>(p, ctl, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
   } else {
     // ===================================== epilogue (16 warps) =====================================
+    // Address and border-class arithmetic is split by how often it changes (the round-1 loop redid 64-bit pixel
+    // addresses and nine bounds tests per sub-tile and ~70 instructions per item in every warp):
+    //   per kernel : the lane's place in an item — image slot, row, column — and its byte offset from the item's origin
+    //   per item   : the origin (warp-uniform: item digits and parameters only), the lane's row class, row validity
+    //   per sub-tile: column class and validity (a few 32-bit operations)
+    //   per unit   : one 32-bit offset each for the bias words and the store
     const int q = warp & 3, h = warp >> 2;
     const int g = 4 * q + (lane >> 3), px = lane & 7;  // row group and column of this thread's TMEM lane
     const int img = g / p.Q, oyl = g - img * p.Q;
+    // byte offset of this lane's pixel from the item's first pixel (image n0, row oy0, column ox0); items span at most a
+    // few images, so 32 bits suffice (host-checked: nb * out_h * out_w * out_stride < 2^31)
+    const uint32_t lane_off = (uint32_t) ((img * p.out_h + oyl) * p.out_w + px) * (uint32_t) p.out_stride;
+    const uint32_t sub_step = 8u * (uint32_t) p.out_stride;  // one sub-tile (8 columns) further
     int as = 0;
     uint32_t as_phase = 0;
     ItemPos pos = first_pos(p, first);
     for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
       const DwItem it = make_item(p, pos);
-      const int n = it.n0 + img, oy = it.oy0 + oyl;
-      const bool row_ok = img < p.nb && n < p.batch && oy < p.out_h;
+      const int c0 = it.cb * p.G * 16;
+      // warp-uniform origin of the item in the output tensor
+      uint8_t* const obase = p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w + it.ox0) * p.out_stride + c0;
+      const int oy = it.oy0 + oyl;
+      const bool row_ok = img < p.nb && it.n0 + img < p.batch && oy < p.out_h;
+      // row class: bit k set iff input row iy0 + k lies inside the image (taps below 0 / at or above in_h are padding)
       const int iy0 = oy * S - p.pad_top;
-      const int rm = (iy0 >= 0 && iy0 < p.in_h ? 1 : 0) | (iy0 + 1 >= 0 && iy0 + 1 < p.in_h ? 2 : 0) |
-          (iy0 + 2 >= 0 && iy0 + 2 < p.in_h ? 4 : 0);
-      uint8_t* orow = p.out + ((size_t) ((long long) n * p.out_h + oy) * p.out_w) * p.out_stride;
+      const int rlo = iy0 < 0 ? -iy0 : 0, rhi = iy0 + 3 - p.in_h > 0 ? iy0 + 3 - p.in_h : 0;
+      const uint32_t rm = rhi >= 3 ? 0u : (((7u << rlo) & 7u) & (7u >> rhi));
+      const uint32_t bias_row = rm * 8u * (uint32_t) p.channels + (uint32_t) c0;  // index into bias_cls, column class 0
       const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
-      if (p.epi_poll_ns > 0) {
-        mbar_wait_relaxed(smem_u32(&ctl.tmem_full[as]), as_phase, (uint32_t) p.epi_poll_ns);
-      } else {
-        mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
-      }
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
       tc_fence_after_sync();
       const uint32_t tbase = tmem_base + (uint32_t) as * p.acc_stride + ((uint32_t) (q * 32) << 16);
-      // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, gi fastest); pixel, border-class
-      // and address arithmetic are redone only when j changes
+      // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, j fastest); the per-sub-tile
+      // values are redone only when j changes
       const int units = it.mt_eff * it.g_eff;
       const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
       if (h >= units) {  // nothing to read (narrow tail item)
@@ -342,8 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(empty_bar);
       }
       int j_cur = -1;
-      const int32_t* bias = nullptr;
-      uint8_t* dst = nullptr;
+      uint32_t bias_idx = 0, dst_off = 0;
       bool valid = false;
       for (int un = h; un < units; un += 4) {
         int j, gi;
@@ -352,15 +366,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           j_cur = j;
           const int ox = it.ox0 + 8 * j + px;
           const int ix0 = ox * S - p.pad_left;
-          const int cm = (ix0 >= 0 && ix0 < p.in_w ? 1 : 0) | (ix0 + 1 >= 0 && ix0 + 1 < p.in_w ? 2 : 0) |
-              (ix0 + 2 >= 0 && ix0 + 2 < p.in_w ? 4 : 0);
-          const int c0 = it.cb * p.G * 16;
-          bias = p.bias_cls + (size_t) (rm * 8 + cm) * p.channels + c0;
-          dst = orow + (size_t) ox * p.out_stride + c0;
+          const int clo = ix0 < 0 ? -ix0 : 0, chi = ix0 + 3 - p.in_w > 0 ? ix0 + 3 - p.in_w : 0;
+          const uint32_t cm = chi >= 3 ? 0u : (((7u << clo) & 7u) & (7u >> chi));
+          bias_idx = bias_row + cm * (uint32_t) p.channels;
+          dst_off = lane_off + (uint32_t) j * sub_step;
           valid = row_ok && ox < p.out_w;
         }
-        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, bias + gi * 16, dst + gi * 16, valid, un + 4 >= units,
-                              empty_bar);
+        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, p.bias_cls + (bias_idx + (uint32_t) gi * 16u),
+                              obase + (dst_off + (uint32_t) gi * 16u), valid, un + 4 >= units, empty_bar);
       }
       as ^= 1;
       if (as == 0) as_phase ^= 1;
@@ -376,11 +389,19 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+// Raises the kernel's dynamic shared-memory limit to everything the device allows beside its static shared memory.
+static cudaError_t set_max_dynamic_smem(const void* kern, int max_smem_optin) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - (int) fa.sharedSizeBytes);
+}
+
 template <int S, int RQ, int NB>
 cudaError_t launch_one(const DwTcParams& p, const CUtensorMap& tm, int grid, int max_smem_optin, cudaStream_t stream) {
   auto kern = q8_dwconv3x3_umma_kernel<S, RQ, NB>;
   // once per instantiation, to the device maximum (a per-launch value raced between host threads; see the igemm launcher)
-  static cudaError_t attr_status = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+  static cudaError_t attr_status = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), max_smem_optin);
   if (attr_status != cudaSuccess) return attr_status;
   kern<<<grid, kThreads, p.smem_total, stream>>>(p, tm);
   return cudaGetLastError();

@@ -1133,13 +1133,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 // ------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------
+// Raises the kernel's dynamic shared-memory limit to everything the device allows beside its static shared memory.
+static cudaError_t set_max_dynamic_smem(const void* kern, int max_smem_optin) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - (int) fa.sharedSizeBytes);
+}
+
 // The dynamic-smem limit is a property of the kernel instantiation, not of a launch: it is raised ONCE to the device's
 // opt-in maximum (setting it per launch to the operator's size raced between host threads running different operators).
 template <int MODE, int VEC>
 static cudaError_t launch_one(const IgemmParams& p, const CUtensorMap& tmap, const IgemmStoreMaps& smaps, int grid,
                               int max_smem_optin, cudaStream_t stream) {
   auto kern = q8_igemm_kernel<MODE, VEC>;
-  static cudaError_t attr_status = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+  static cudaError_t attr_status = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), max_smem_optin);
   if (attr_status != cudaSuccess) return attr_status;
   kern<<<grid, kThreads, p.smem_total, stream>>>(p, tmap, smaps);
   return cudaGetLastError();
