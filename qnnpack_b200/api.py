@@ -109,6 +109,24 @@ class QnnpackLibrary:
     def setup_fully_connected(self, op, batch, x, in_stride, out, out_stride):
         return self.lib.qnnp_setup_fully_connected_nc_q8(op, batch, _ptr(x), in_stride, _ptr(out), out_stride)
 
+    # -- the operators beside the convolution path: one generic driver ---------------------------------
+    def create(self, name: str, *args):
+        """qnnp_create_<name>(*args, flags=0, &op) -> (status, op)"""
+        op = _capi.op_t()
+        fn = getattr(self.lib, f"qnnp_create_{name}")
+        cargs = [float(np.float32(a)) if isinstance(a, (float, np.floating)) else (_ptr(a) if isinstance(a, np.ndarray) else a)
+                 for a in args]
+        return fn(*cargs, 0, C.byref(op)), op
+
+    def setup(self, name: str, op, *args, threadpool=False):
+        """qnnp_setup_<name>(op, *args[, threadpool]); NumPy arrays become pointers, device addresses are passed as
+        ctypes.c_void_p(address)."""
+        fn = getattr(self.lib, f"qnnp_setup_{name}")
+        cargs = [_ptr(a) if isinstance(a, np.ndarray) else a for a in args]
+        if threadpool:
+            cargs.append(self.pool)
+        return fn(op, *cargs)
+
     def run(self, op):
         return self.lib.qnnp_run_operator(op, self.pool)
 

@@ -16,8 +16,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libqnnpack.so")
 
 SOURCES = ["qnnpack_api.cu", "q8_igemm_sm100.cu", "q8_dwconv_sm100.cu", "q8_dwconv_stream_sm100.cu",
-           "q8_dwconv_umma_sm100.cu", "q8_peak_sm100.cu"]
-HEADERS = ["q8_igemm_sm100.cuh", "q8_dwconv_sm100.cuh", "sm100_ptx.cuh", "requant_math.h", "requant_dev.cuh",
+           "q8_dwconv_umma_sm100.cu", "q8_peak_sm100.cu", "q8_eltwise_sm100.cu"]
+HEADERS = ["q8_igemm_sm100.cuh", "q8_dwconv_sm100.cuh", "q8_eltwise_sm100.cuh", "sm100_ptx.cuh", "requant_math.h", "requant_dev.cuh",
            os.path.join("..", "..", "include", "qnnpack.h"), os.path.join("..", "..", "include", "qnnpack_cuda.h")]
 
 NVCC_FLAGS = [

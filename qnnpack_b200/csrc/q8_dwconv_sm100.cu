@@ -184,10 +184,22 @@ __global__ void __launch_bounds__(256) q8_direct_conv_kernel(const __grid_consta
   const uint8_t* wrow = p.w + (size_t) och * p.kh * p.kw * p.gic;
   int32_t acc = __ldg(p.bias + och);  // folded bias: padded taps read izp
   for (int ky = 0; ky < p.kh; ky++) {
-    const int iy = oy * p.stride_h + ky * p.dil_h - p.pad_top;
+    int iy = oy * p.stride_h + ky * p.dil_h - p.pad_top;
+    bool oky = true;
+    if (p.deconv) {  // src/indirection.c:165-178: y = oy + pad_top - ky*dil must be a non-negative multiple of the stride
+      const int y = oy + p.pad_top - ky * p.dil_h;
+      iy = y / p.stride_h;
+      oky = y >= 0 && iy * p.stride_h == y;
+    }
     for (int kx = 0; kx < p.kw; kx++) {
-      const int ix = ox * p.stride_w + kx * p.dil_w - p.pad_left;
-      const bool ok = (unsigned) iy < (unsigned) p.in_h && (unsigned) ix < (unsigned) p.in_w;
+      int ix = ox * p.stride_w + kx * p.dil_w - p.pad_left;
+      bool okx = true;
+      if (p.deconv) {
+        const int x = ox + p.pad_left - kx * p.dil_w;
+        ix = x / p.stride_w;
+        okx = x >= 0 && ix * p.stride_w == x;
+      }
+      const bool ok = oky && okx && (unsigned) iy < (unsigned) p.in_h && (unsigned) ix < (unsigned) p.in_w;
       const uint8_t* a = p.in + (((size_t) n * p.in_h + (ok ? iy : 0)) * p.in_w + (ok ? ix : 0)) * p.in_stride +
           (size_t) g * p.gic;
       const uint8_t* wk = wrow + (size_t) (ky * p.kw + kx) * p.gic;

@@ -88,6 +88,8 @@ struct DirectParams {
   int in_h, in_w, out_h, out_w, kh, kw;
   int stride_h, stride_w, dil_h, dil_w, pad_top, pad_left;
   int izp, kzp;
+  int deconv;           // 1: transposed convolution — tap (ky, kx) of output (oy, ox) reads input ((oy + pad_top - ky*dil) / stride, ..)
+                        // when the division is exact and in range (src/indirection.c:134-190), else it contributes nothing
   Q8Requant rq;
 };
 

@@ -21,12 +21,14 @@
 #include <string.h>
 
 #include <atomic>
+#include <initializer_list>
 #include <new>
 #include <vector>
 
 #include "../../include/qnnpack.h"
 #include "../../include/qnnpack_cuda.h"
 #include "q8_dwconv_sm100.cuh"
+#include "q8_eltwise_sm100.cuh"
 #include "q8_igemm_sm100.cuh"
 #include "requant_dev.cuh"
 
@@ -316,7 +318,11 @@ int pow2_align(uintptr_t v, int cap) {  // largest power of two <= cap dividing 
   return a;
 }
 
-enum KernelKind { kKindNone = 0, kKindIgemmGemm, kKindIgemmConv, kKindDw3x3, kKindDirect };
+enum KernelKind {
+  kKindNone = 0, kKindIgemmGemm, kKindIgemmConv, kKindDw3x3, kKindDirect,
+  // operators beside the convolution path (q8_eltwise_sm100.cu)
+  kKindAdd, kKindGavgPool, kKindAvgPool, kKindMaxPool, kKindClamp, kKindLut, kKindSoftargmax, kKindShuffle
+};
 
 }  // namespace
 
@@ -364,6 +370,23 @@ struct qnnp_operator {
   uint8_t* output = nullptr;
   size_t in_stride = 0, out_stride = 0;
   bool in_on_device = false, out_on_device = false;
+  // element-wise / pooling operators
+  bool is_deconv = false;        // kKindDirect: transposed convolution (src/deconvolution.c)
+  uint32_t adj_h = 0, adj_w = 0; // deconvolution output adjustment
+  size_t channels = 0;           // nc / nwc operators
+  const uint8_t* input2 = nullptr;
+  size_t in2_stride = 0;
+  bool in2_on_device = false;
+  uint8_t* d_in2 = nullptr;
+  size_t d_in2_cap = 0;
+  q8::AddParams add{};           // quantisation fields filled at create
+  q8::AvgQuant avgq{};
+  float in_scale = 0.f, out_scale = 0.f;
+  uint8_t ozp = 0, omin = 0, omax = 255;
+  uint8_t* d_lut = nullptr;      // 256-entry table (sigmoid, leaky ReLU)
+  uint32_t* d_table32 = nullptr; // softargmax: 511 entries
+  size_t in_span = 0, in2_span = 0, out_span = 0;  // bytes the operator reads / writes (host staging)
+  bool out_dense = true;         // the output has no gaps between pixels / rows (else staging must preserve them)
   struct qnnp_launch_plan* plan = nullptr;  // cached launch state (built in setup / first run; see build_plan)
   // staging for host pointers
   uint8_t* d_in = nullptr;
@@ -383,6 +406,9 @@ void free_operator(qnnp_operator* op) {
   cudaFree(op->d_dwtc_bias);
   cudaFree(op->d_in);
   cudaFree(op->d_out);
+  cudaFree(op->d_in2);
+  cudaFree(op->d_lut);
+  cudaFree(op->d_table32);
   delete_plan(op->plan);
   delete op;
 }
@@ -777,7 +803,10 @@ enum qnnp_status pack_direct(qnnp_operator* op, const uint8_t* kernel, const int
 // the plan is built, never on the launch path.  (Round 1 redid all of it, ~10 getenv() calls and a tensor-map encode
 // included, on every run: SURVEY.md §3.4 puts this work in setup, like the reference's indirection-buffer setup,
 // src/convolution.c:428-492.)
-enum PlanPath { kPlanNone = 0, kPlanIgemm, kPlanDwUmma, kPlanDwStream, kPlanDwGeneric, kPlanDirect };
+enum PlanPath {
+  kPlanNone = 0, kPlanIgemm, kPlanDwUmma, kPlanDwStream, kPlanDwGeneric, kPlanDirect,
+  kPlanAdd, kPlanGavgPool, kPlanPool2d, kPlanMap, kPlanSoftargmax, kPlanShuffle
+};
 
 bool env_set(const char* name) { return getenv(name) != nullptr; }
 
@@ -832,18 +861,35 @@ struct qnnp_launch_plan {
   int dw_cv = 1;
   // direct
   q8::DirectParams dir{};
+  // element-wise / pooling
+  const uint8_t* in2 = nullptr;
+  int vec = 1;
+  bool flag = false;  // map: table lookup; pool2d: max
+  q8::AddParams add{};
+  q8::MapParams map{};
+  q8::ShuffleParams shuf{};
+  q8::SoftargmaxParams soft{};
+  q8::GavgParams gavg{};
+  q8::PoolParams pool{};
 };
 
 void delete_plan(qnnp_launch_plan* p) { delete p; }
 
 namespace {
 
-enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, uint8_t* out) {
+// widest piece size in {16, 4, 1} bytes that divides every given address / stride / length
+int common_vec(std::initializer_list<uintptr_t> values) {
+  int v = 16;
+  for (uintptr_t x : values) v = pow2_align(x, v);
+  return v >= 16 ? 16 : (v >= 4 ? 4 : 1);
+}
+
+enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t* in2, uint8_t* out) {
   if (op->plan == nullptr) op->plan = new (std::nothrow) qnnp_launch_plan();
   if (op->plan == nullptr) return qnnp_status_out_of_memory;
   qnnp_launch_plan& pl = *op->plan;
   pl.valid = false;
-  pl.in = in, pl.out = out;
+  pl.in = in, pl.in2 = in2, pl.out = out;
   const size_t M = op->batch * op->out_h * op->out_w;
   switch (op->kind) {
     case kKindIgemmGemm:
@@ -1045,8 +1091,102 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, uint8_t* out) 
       p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
+      p.deconv = op->is_deconv ? 1 : 0;
       pl.dir = p;
       pl.path = kPlanDirect;
+      break;
+    }
+    case kKindAdd: {
+      q8::AddParams p = op->add;
+      p.a = in, p.b = in2, p.y = out;
+      p.a_stride = (long long) op->in_stride, p.b_stride = (long long) op->in2_stride, p.y_stride = (long long) op->out_stride;
+      const bool dense = op->in_stride == op->channels && op->in2_stride == op->channels && op->out_stride == op->channels;
+      // dense rows form one long row: pieces may then straddle row boundaries
+      const size_t row_len = dense ? op->batch * op->channels : op->channels;
+      pl.vec = common_vec({(uintptr_t) in, (uintptr_t) in2, (uintptr_t) out, (uintptr_t) row_len,
+                           dense ? 0 : (uintptr_t) op->in_stride, dense ? 0 : (uintptr_t) op->in2_stride,
+                           dense ? 0 : (uintptr_t) op->out_stride});
+      p.rows = dense ? 1 : (long long) op->batch;
+      if (row_len / pl.vec >= (1ull << 31)) {  // keep the per-row piece count in 32 bits
+        p.rows = (long long) op->batch, pl.vec = common_vec({(uintptr_t) in, (uintptr_t) in2, (uintptr_t) out, (uintptr_t) op->channels});
+        p.pieces_per_row = (int) (op->channels / pl.vec);
+      } else {
+        p.pieces_per_row = (int) (row_len / pl.vec);
+      }
+      pl.add = p;
+      pl.path = kPlanAdd;
+      break;
+    }
+    case kKindClamp:
+    case kKindLut: {
+      q8::MapParams p{};
+      p.x = in, p.y = out, p.lut = op->d_lut;
+      p.x_stride = (long long) op->in_stride, p.y_stride = (long long) op->out_stride;
+      p.lo = op->omin, p.hi = op->omax;
+      const bool dense = op->in_stride == op->channels && op->out_stride == op->channels;
+      const size_t row_len = dense ? op->batch * op->channels : op->channels;
+      pl.vec = common_vec({(uintptr_t) in, (uintptr_t) out, (uintptr_t) row_len, dense ? 0 : (uintptr_t) op->in_stride,
+                           dense ? 0 : (uintptr_t) op->out_stride});
+      p.rows = dense ? 1 : (long long) op->batch;
+      if (row_len / pl.vec >= (1ull << 31)) {
+        p.rows = (long long) op->batch, pl.vec = common_vec({(uintptr_t) in, (uintptr_t) out, (uintptr_t) op->channels});
+        p.pieces_per_row = (int) (op->channels / pl.vec);
+      } else {
+        p.pieces_per_row = (int) (row_len / pl.vec);
+      }
+      pl.map = p;
+      pl.flag = op->kind == kKindLut;
+      pl.path = kPlanMap;
+      break;
+    }
+    case kKindShuffle: {
+      q8::ShuffleParams p{};
+      p.x = in, p.y = out;
+      p.rows = (long long) op->batch, p.x_stride = (long long) op->in_stride, p.y_stride = (long long) op->out_stride;
+      p.groups = (int) op->groups, p.group_channels = (int) op->gic;
+      pl.shuf = p;
+      pl.path = kPlanShuffle;
+      break;
+    }
+    case kKindSoftargmax: {
+      q8::SoftargmaxParams p{};
+      p.x = in, p.y = out, p.table = op->d_table32;
+      p.rows = (long long) op->batch, p.x_stride = (long long) op->in_stride, p.y_stride = (long long) op->out_stride;
+      p.channels = (int) op->channels;
+      pl.soft = p;
+      pl.path = kPlanSoftargmax;
+      break;
+    }
+    case kKindGavgPool: {
+      q8::GavgParams p{};
+      p.x = in, p.y = out;
+      p.batch = (long long) op->batch, p.width = (long long) op->in_w;
+      p.x_stride = (long long) op->in_stride, p.y_stride = (long long) op->out_stride;
+      p.channels = (int) op->channels;
+      p.bias = (int32_t) (0u - (uint32_t) op->in_w * (uint32_t) op->izp);  // src/global-average-pooling.c:137
+      p.q = op->avgq;
+      pl.vec = common_vec({(uintptr_t) in, (uintptr_t) out, (uintptr_t) op->channels, (uintptr_t) op->in_stride,
+                           (uintptr_t) op->out_stride}) >= 4 ? 4 : 1;
+      pl.gavg = p;
+      pl.path = kPlanGavgPool;
+      break;
+    }
+    case kKindAvgPool:
+    case kKindMaxPool: {
+      q8::PoolParams p{};
+      p.x = in, p.y = out;
+      p.batch = (long long) op->batch, p.x_stride = (long long) op->in_stride, p.y_stride = (long long) op->out_stride;
+      p.channels = (int) op->channels;
+      p.in_h = (int) op->in_h, p.in_w = (int) op->in_w, p.out_h = (int) op->out_h, p.out_w = (int) op->out_w;
+      p.kh = (int) op->kh, p.kw = (int) op->kw, p.stride_h = (int) op->stride_h, p.stride_w = (int) op->stride_w;
+      p.dil_h = (int) op->dil_h, p.dil_w = (int) op->dil_w, p.pad_top = (int) op->pad_top, p.pad_left = (int) op->pad_left;
+      p.izp = op->izp, p.bias = 0, p.lo = op->omin, p.hi = op->omax;
+      p.q = op->avgq;
+      pl.vec = common_vec({(uintptr_t) in, (uintptr_t) out, (uintptr_t) op->channels, (uintptr_t) op->in_stride,
+                           (uintptr_t) op->out_stride}) >= 4 ? 4 : 1;
+      pl.flag = op->kind == kKindMaxPool;
+      pl.pool = p;
+      pl.path = kPlanPool2d;
       break;
     }
     default:
@@ -1056,9 +1196,9 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, uint8_t* out) 
   return qnnp_status_success;
 }
 
-enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cudaStream_t stream) {
-  if (op->plan == nullptr || !op->plan->valid || op->plan->in != in || op->plan->out != out) {
-    const enum qnnp_status st = build_plan(op, in, out);
+enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, const uint8_t* in2, uint8_t* out, cudaStream_t stream) {
+  if (op->plan == nullptr || !op->plan->valid || op->plan->in != in || op->plan->in2 != in2 || op->plan->out != out) {
+    const enum qnnp_status st = build_plan(op, in, in2, out);
     if (st != qnnp_status_success) return st;
   }
   const qnnp_launch_plan& pl = *op->plan;
@@ -1075,6 +1215,12 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, uint8_t* out, cuda
     case kPlanDwStream: e = q8::launch_q8_dwconv3x3_stream(pl.sp, stream); break;
     case kPlanDwGeneric: e = q8::launch_q8_dwconv3x3(pl.dp, pl.dw_cv, stream); break;
     case kPlanDirect: e = q8::launch_q8_direct_conv(pl.dir, stream); break;
+    case kPlanAdd: e = q8::launch_q8_add(pl.add, pl.vec, stream); break;
+    case kPlanMap: e = q8::launch_q8_map(pl.map, pl.vec, pl.flag, stream); break;
+    case kPlanShuffle: e = q8::launch_q8_shuffle(pl.shuf, stream); break;
+    case kPlanSoftargmax: e = q8::launch_q8_softargmax(pl.soft, stream); break;
+    case kPlanGavgPool: e = q8::launch_q8_gavgpool(pl.gavg, pl.vec, stream); break;
+    case kPlanPool2d: e = q8::launch_q8_pool2d(pl.pool, pl.vec, pl.flag, stream); break;
     default: return qnnp_status_invalid_parameter;
   }
   g_lib.launches.fetch_add(1);
@@ -1097,40 +1243,47 @@ enum qnnp_status run_impl(qnnp_operator* op, bool async) {
   if (op->batch == 0) return qnnp_status_success;  // src/operator-run.c:642
   bind_device();
   cudaStream_t stream = g_lib.stream;
-  if (op->in_on_device && op->out_on_device) {
-    enum qnnp_status st = launch(op, op->input, op->output, stream);
+  const bool two_inputs = op->kind == kKindAdd;
+  if (op->in_on_device && op->out_on_device && (!two_inputs || op->in2_on_device)) {
+    enum qnnp_status st = launch(op, op->input, op->input2, op->output, stream);
     if (st != qnnp_status_success || async) return st;
     return map_cuda(cudaStreamSynchronize(stream), "stream synchronize");
   }
   if (async) return qnnp_status_invalid_parameter;
 
-  // host pointers: stage through device buffers inside the (synchronous) call
-  const size_t pixels_in = op->batch * op->in_h * op->in_w, pixels_out = op->batch * op->out_h * op->out_w;
-  const size_t in_bytes = (pixels_in - 1) * op->in_stride + op->groups * op->gic;
-  const size_t out_bytes = (pixels_out - 1) * op->out_stride + op->groups * op->goc;
+  // host pointers: stage through device buffers inside the (synchronous) call.  Pinned (page-locked) host memory makes
+  // these copies truly asynchronous DMA transfers; pageable memory goes through the driver's bounce buffers.
   const uint8_t* din = op->input;
+  const uint8_t* din2 = op->input2;
   uint8_t* dout = op->output;
   enum qnnp_status st;
   if (!op->in_on_device) {
-    if ((st = ensure_capacity(&op->d_in, &op->d_in_cap, in_bytes)) != qnnp_status_success) return st;
-    if ((st = map_cuda(cudaMemcpyAsync(op->d_in, op->input, in_bytes, cudaMemcpyHostToDevice, stream), "H2D input")) !=
+    if ((st = ensure_capacity(&op->d_in, &op->d_in_cap, op->in_span)) != qnnp_status_success) return st;
+    if ((st = map_cuda(cudaMemcpyAsync(op->d_in, op->input, op->in_span, cudaMemcpyHostToDevice, stream), "H2D input")) !=
         qnnp_status_success)
       return st;
     din = op->d_in;
   }
+  if (two_inputs && !op->in2_on_device) {
+    if ((st = ensure_capacity(&op->d_in2, &op->d_in2_cap, op->in2_span)) != qnnp_status_success) return st;
+    if ((st = map_cuda(cudaMemcpyAsync(op->d_in2, op->input2, op->in2_span, cudaMemcpyHostToDevice, stream), "H2D input 2")) !=
+        qnnp_status_success)
+      return st;
+    din2 = op->d_in2;
+  }
   if (!op->out_on_device) {
-    if ((st = ensure_capacity(&op->d_out, &op->d_out_cap, out_bytes)) != qnnp_status_success) return st;
+    if ((st = ensure_capacity(&op->d_out, &op->d_out_cap, op->out_span)) != qnnp_status_success) return st;
     dout = op->d_out;
-    if (op->out_stride != op->groups * op->goc) {
+    if (!op->out_dense) {
       // bytes between pixels must survive untouched, as in the reference (ukernels store exactly N bytes)
-      if ((st = map_cuda(cudaMemcpyAsync(op->d_out, op->output, out_bytes, cudaMemcpyHostToDevice, stream),
+      if ((st = map_cuda(cudaMemcpyAsync(op->d_out, op->output, op->out_span, cudaMemcpyHostToDevice, stream),
                          "H2D output gaps")) != qnnp_status_success)
         return st;
     }
   }
-  if ((st = launch(op, din, dout, stream)) != qnnp_status_success) return st;
+  if ((st = launch(op, din, din2, dout, stream)) != qnnp_status_success) return st;
   if (!op->out_on_device) {
-    if ((st = map_cuda(cudaMemcpyAsync(op->output, op->d_out, out_bytes, cudaMemcpyDeviceToHost, stream), "D2H output")) !=
+    if ((st = map_cuda(cudaMemcpyAsync(op->output, op->d_out, op->out_span, cudaMemcpyDeviceToHost, stream), "D2H output")) !=
         qnnp_status_success)
       return st;
   }
@@ -1139,13 +1292,19 @@ enum qnnp_status run_impl(qnnp_operator* op, bool async) {
 
 // Common tail of qnnp_setup_*: classify the pointers and, when the operator can run zero-copy, build its launch plan now
 // (tensor maps, tiling, kernel variant) so that qnnp_run_operator only launches.
-enum qnnp_status finish_setup(qnnp_operator* op) {
+enum qnnp_status finish_setup(qnnp_operator* op, size_t in_pixels, size_t in_width, size_t out_pixels, size_t out_width) {
+  // spans: (pixels - 1) * stride + bytes used in the last pixel
+  op->in_span = (in_pixels - 1) * op->in_stride + in_width;
+  op->in2_span = op->kind == kKindAdd ? (in_pixels - 1) * op->in2_stride + in_width : 0;
+  op->out_span = (out_pixels - 1) * op->out_stride + out_width;
+  op->out_dense = op->out_stride == out_width;
   op->in_on_device = is_device_pointer(op->input);
   op->out_on_device = is_device_pointer(op->output);
+  op->in2_on_device = op->kind == kKindAdd ? is_device_pointer(op->input2) : false;
   if (op->plan != nullptr) op->plan->valid = false;
-  if (op->in_on_device && op->out_on_device) {
+  if (op->in_on_device && op->out_on_device && (op->kind != kKindAdd || op->in2_on_device)) {
     bind_device();
-    return build_plan(op, op->input, op->output);
+    return build_plan(op, op->input, op->input2, op->output);
   }
   return qnnp_status_success;
 }
@@ -1276,7 +1435,8 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_convolution2d_nhwc_q8(
   op->out_h = output_dimension(op->pad_top + input_height + op->pad_bottom, op->kh, op->dil_h, op->stride_h);
   op->out_w = output_dimension(op->pad_left + input_width + op->pad_right, op->kw, op->dil_w, op->stride_w);
   op->output = output, op->out_stride = output_stride;
-  return finish_setup(op);
+  return finish_setup(op, op->batch * op->in_h * op->in_w, op->groups * op->gic, op->batch * op->out_h * op->out_w,
+                      op->groups * op->goc);
 }
 
 QNNP_EXPORT enum qnnp_status qnnp_create_fully_connected_nc_q8(
@@ -1335,7 +1495,7 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_fully_connected_nc_q8(
   op->in_h = batch_size, op->in_w = 1, op->out_h = batch_size, op->out_w = 1;
   op->input = input, op->in_stride = input_stride;
   op->output = output, op->out_stride = output_stride;
-  return finish_setup(op);
+  return finish_setup(op, batch_size, op->gic, batch_size, op->goc);
 }
 
 QNNP_EXPORT enum qnnp_status qnnp_run_operator(qnnp_operator_t op, pthreadpool_t threadpool) {
@@ -1499,44 +1659,543 @@ QNNP_EXPORT enum qnnp_status qnnp_cuda_requantize_q31(
   return map_cuda(e, "qnnp_cuda_requantize_q31");
 }
 
-// ---- operators outside the q8 hot path: link-compatible stubs ---------------------------------------
-#define QNNP_UNSUPPORTED(name, ...)                                                                   \
-  QNNP_EXPORT enum qnnp_status name(__VA_ARGS__) {                                                     \
-    if (!g_lib.initialized) return qnnp_status_uninitialized;                                          \
-    log_error(#name " is not on the q8gemm/q8conv/q8dwconv hot path and is not implemented in this library"); \
-    return qnnp_status_unsupported_parameter;                                                          \
-  }
+// ================================================================================================
+// operators beside the convolution path: each mirrors the reference's validation order
+// and status codes; quantisation parameters restate src/qnnpack/requantization.h with the same fp32 operations.
+// ================================================================================================
+namespace {
 
-QNNP_UNSUPPORTED(qnnp_create_deconvolution2d_nhwc_q8, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                 uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, size_t, size_t, uint8_t, float, uint8_t, float,
-                 const uint8_t*, const int32_t*, uint8_t, float, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_deconvolution2d_nhwc_q8, qnnp_operator_t, size_t, size_t, size_t, const uint8_t*, size_t,
-                 uint8_t*, size_t, pthreadpool_t)
-QNNP_UNSUPPORTED(qnnp_create_global_average_pooling_nwc_q8, size_t, uint8_t, float, uint8_t, float, uint8_t, uint8_t,
-                 uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_global_average_pooling_nwc_q8, qnnp_operator_t, size_t, size_t, const uint8_t*, size_t,
-                 uint8_t*, size_t)
-QNNP_UNSUPPORTED(qnnp_create_average_pooling2d_nhwc_q8, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                 uint32_t, uint32_t, size_t, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_average_pooling2d_nhwc_q8, qnnp_operator_t, size_t, size_t, size_t, const uint8_t*, size_t,
-                 uint8_t*, size_t, pthreadpool_t)
-QNNP_UNSUPPORTED(qnnp_create_max_pooling2d_nhwc_u8, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
-                 uint32_t, uint32_t, uint32_t, size_t, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_max_pooling2d_nhwc_u8, qnnp_operator_t, size_t, size_t, size_t, const uint8_t*, size_t,
-                 uint8_t*, size_t, pthreadpool_t)
-QNNP_UNSUPPORTED(qnnp_create_channel_shuffle_nc_x8, size_t, size_t, uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_channel_shuffle_nc_x8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
-QNNP_UNSUPPORTED(qnnp_create_add_nc_q8, size_t, uint8_t, float, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t,
-                 qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_add_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, const uint8_t*, size_t, uint8_t*,
-                 size_t)
-QNNP_UNSUPPORTED(qnnp_create_clamp_nc_u8, size_t, uint8_t, uint8_t, uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_clamp_nc_u8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
-QNNP_UNSUPPORTED(qnnp_create_sigmoid_nc_q8, size_t, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t,
-                 qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_sigmoid_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
-QNNP_UNSUPPORTED(qnnp_create_leaky_relu_nc_q8, size_t, float, uint8_t, float, uint8_t, float, uint8_t, uint8_t, uint32_t,
-                 qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_leaky_relu_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
-QNNP_UNSUPPORTED(qnnp_create_softargmax_nc_q8, size_t, float, uint8_t, float, uint32_t, qnnp_operator_t*)
-QNNP_UNSUPPORTED(qnnp_setup_softargmax_nc_q8, qnnp_operator_t, size_t, const uint8_t*, size_t, uint8_t*, size_t)
+float f32_from_bits(uint32_t u) {
+  float f;
+  memcpy(&f, &u, sizeof f);
+  return f;
+}
+
+// qnnp_compute_avgpool_quantization_params, scalar member (src/qnnpack/requantization.h:200-265)
+q8::AvgQuant make_avg_quant(float scale, uint8_t ozp, uint8_t omin, uint8_t omax) {
+  const uint32_t bits = f32_bits(scale);
+  q8::AvgQuant q;
+  q.multiplier = (int32_t) ((bits & 0x007FFFFFu) | 0x00800000u);
+  const int32_t shift = 127 + 23 - (int32_t) (bits >> 23);
+  q.right_shift = (uint32_t) shift;
+  q.rounding = (int64_t) 1 << (shift - 1);
+  q.min_less_zp = (int32_t) omin - (int32_t) ozp;
+  q.max_less_zp = (int32_t) omax - (int32_t) ozp;
+  q.zero_point = ozp;
+  return q;
+}
+
+qnnp_operator* new_operator(KernelKind kind) {
+  qnnp_operator* op = new (std::nothrow) qnnp_operator();
+  if (op != nullptr) op->kind = kind;
+  return op;
+}
+
+enum qnnp_status upload(void** dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMalloc(dst, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  return map_cuda(e, "uploading operator table");
+}
+
+// nc operators: batch rows of `channels` bytes
+enum qnnp_status setup_nc(qnnp_operator* op, size_t batch, const uint8_t* x, size_t x_stride, uint8_t* y, size_t y_stride) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr) return qnnp_status_invalid_parameter;
+  if (batch == 0) {
+    op->batch = 0;
+    if (op->plan != nullptr) op->plan->valid = false;
+    return qnnp_status_success;
+  }
+  op->batch = batch;
+  op->input = x, op->in_stride = x_stride;
+  op->output = y, op->out_stride = y_stride;
+  return finish_setup(op, batch, op->channels, batch, op->channels);
+}
+
+}  // namespace
+
+// ---- deconvolution (src/deconvolution.c:38-277): the direct kernel with the transposed tap mapping ----------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_deconvolution2d_nhwc_q8(
+    uint32_t input_padding_top, uint32_t input_padding_right, uint32_t input_padding_bottom, uint32_t input_padding_left,
+    uint32_t adjustment_height, uint32_t adjustment_width, uint32_t kernel_height, uint32_t kernel_width, uint32_t stride_height,
+    uint32_t stride_width, uint32_t dilation_height, uint32_t dilation_width, uint32_t groups, size_t group_input_channels,
+    size_t group_output_channels, uint8_t input_zero_point, float input_scale, uint8_t kernel_zero_point, float kernel_scale,
+    const uint8_t* kernel, const int32_t* bias, uint8_t output_zero_point, float output_scale, uint8_t output_min,
+    uint8_t output_max, uint32_t flags, qnnp_operator_t* deconvolution_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_deconvolution2d_nhwc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (kernel_width == 0 || kernel_height == 0 || stride_width == 0 || stride_height == 0 || dilation_width == 0 ||
+      dilation_height == 0) {  // src/deconvolution.c:77-96
+    log_error("failed to create deconvolution: kernel, stride and dilation dimensions must be non-zero");
+    return qnnp_status_invalid_parameter;
+  }
+  if (!scale_ok(input_scale) || !scale_ok(kernel_scale) || !scale_ok(output_scale)) {
+    log_error("failed to create deconvolution with %.7g input, %.7g kernel, %.7g output scale: scales must be finite and positive",
+              input_scale, kernel_scale, output_scale);
+    return qnnp_status_invalid_parameter;
+  }
+  const float deconvolution_scale = input_scale * kernel_scale / output_scale;  // src/deconvolution.c:118
+  if (deconvolution_scale >= 1.0f || !(deconvolution_scale >= 0x1.0p-32f)) {
+    log_error("failed to create deconvolution: scale %.7g is outside [2^-32, 1)", deconvolution_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  if (groups == 0 || group_input_channels == 0 || group_output_channels == 0) return qnnp_status_invalid_parameter;
+  bind_device();
+  qnnp_operator* op = new_operator(kKindDirect);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->is_deconv = true;
+  op->pad_top = input_padding_top, op->pad_right = input_padding_right;
+  op->pad_bottom = input_padding_bottom, op->pad_left = input_padding_left;
+  op->adj_h = adjustment_height, op->adj_w = adjustment_width;
+  op->kh = kernel_height, op->kw = kernel_width;
+  op->stride_h = stride_height, op->stride_w = stride_width;
+  op->dil_h = dilation_height, op->dil_w = dilation_width;
+  op->groups = groups, op->gic = group_input_channels, op->goc = group_output_channels;
+  op->izp = input_zero_point, op->kzp = kernel_zero_point;
+  op->rq = q8_make_requant(f32_bits(deconvolution_scale), output_zero_point, output_min, output_max);
+  op->rq_mode = select_rq_mode(op->rq);
+  // the deconvolution kernel is [group][input channel][ky][kx][output channel] (test/deconvolution-operator-tester.h:411,
+  // src/qnnpack/pack.h:93-133); bring it to the convolution layout [group][output channel][ky][kx][input channel]
+  const size_t ks = (size_t) kernel_height * kernel_width;
+  std::vector<uint8_t> kt((size_t) groups * group_output_channels * ks * group_input_channels);
+  for (size_t g = 0; g < groups; g++)
+    for (size_t ic = 0; ic < group_input_channels; ic++)
+      for (size_t t = 0; t < ks; t++)
+        for (size_t oc = 0; oc < group_output_channels; oc++)
+          kt[((g * group_output_channels + oc) * ks + t) * group_input_channels + ic] =
+              kernel[((g * group_input_channels + ic) * ks + t) * group_output_channels + oc];
+  const enum qnnp_status st = pack_direct(op, kt.data(), bias);
+  if (st != qnnp_status_success) {
+    free_operator(op);
+    return st;
+  }
+  *deconvolution_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_deconvolution2d_nhwc_q8(qnnp_operator_t op, size_t batch_size, size_t input_height,
+                                                                size_t input_width, const uint8_t* input, size_t input_stride,
+                                                                uint8_t* output, size_t output_stride, pthreadpool_t threadpool) {
+  (void) threadpool;
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr || !op->is_deconv) return qnnp_status_invalid_parameter;
+  if (batch_size == 0) {
+    op->batch = 0;
+    if (op->plan != nullptr) op->plan->valid = false;
+    return qnnp_status_success;
+  }
+  if (input_width == 0 || input_height == 0) return qnnp_status_invalid_parameter;
+  op->batch = batch_size;
+  op->in_h = input_height, op->in_w = input_width;
+  op->input = input, op->in_stride = input_stride;
+  // src/deconvolution.c:25-36: stride * (in - 1) + adjustment + effective kernel - total padding
+  op->out_h = op->stride_h * (input_height - 1) + op->adj_h + ((op->kh - 1) * op->dil_h + 1) - (op->pad_top + op->pad_bottom);
+  op->out_w = op->stride_w * (input_width - 1) + op->adj_w + ((op->kw - 1) * op->dil_w + 1) - (op->pad_left + op->pad_right);
+  op->output = output, op->out_stride = output_stride;
+  return finish_setup(op, batch_size * input_height * input_width, op->groups * op->gic, batch_size * op->out_h * op->out_w,
+                      op->groups * op->goc);
+}
+
+// ---- add (src/add.c:22-149) ---------------------------------------------------------------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_add_nc_q8(size_t channels, uint8_t a_zero_point, float a_scale, uint8_t b_zero_point,
+                                                   float b_scale, uint8_t sum_zero_point, float sum_scale, uint8_t sum_min,
+                                                   uint8_t sum_max, uint32_t flags, qnnp_operator_t* add_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_add_nc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (channels == 0) {
+    log_error("failed to create add operator with %zu channels: number of channels must be non-zero", channels);
+    return qnnp_status_invalid_parameter;
+  }
+  if (!scale_ok(a_scale) || !scale_ok(b_scale) || !scale_ok(sum_scale)) {
+    log_error("failed to create add operator with %.7g A, %.7g B, %.7g output scale: scales must be finite and positive", a_scale,
+              b_scale, sum_scale);
+    return qnnp_status_invalid_parameter;
+  }
+  if (sum_min >= sum_max) {
+    log_error("failed to create add operator with [%u, %u] output range: range min must be below range max", sum_min, sum_max);
+    return qnnp_status_invalid_parameter;
+  }
+  const float a_output_scale = a_scale / sum_scale, b_output_scale = b_scale / sum_scale;
+  if (a_output_scale < 0x1.0p-14f || a_output_scale >= 0x1.0p+8f || b_output_scale < 0x1.0p-14f || b_output_scale >= 0x1.0p+8f) {
+    log_error("failed to create add operator: scale ratios %.7g / %.7g must be in [2**-14, 2**8)", a_output_scale, b_output_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  qnnp_operator* op = new_operator(kKindAdd);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->channels = channels;
+  // qnnp_compute_add_quantization_params (src/qnnpack/requantization.h:327-414), same fp32 operations in the same order
+  const float max_output_scale = a_output_scale > b_output_scale ? a_output_scale : b_output_scale;
+  const int32_t max_scale_exponent = (int32_t) (f32_bits(max_output_scale) >> 23) - 127;
+  const uint32_t shift = (uint32_t) (21 - max_scale_exponent);
+  const float scale_multiplier = f32_from_bits((uint32_t) (21 - max_scale_exponent + 127) << 23);
+  const uint32_t a_multiplier = (uint32_t) (int32_t) lrintf(a_output_scale * scale_multiplier);
+  const uint32_t b_multiplier = (uint32_t) (int32_t) lrintf(b_output_scale * scale_multiplier);
+  q8::AddParams& q = op->add;
+  q.a_multiplier = a_multiplier, q.b_multiplier = b_multiplier;
+  q.shift = (int32_t) shift;
+  q.remainder_mask = (int32_t) ((1u << shift) - 1u);
+  q.remainder_threshold = (int32_t) (((1u << shift) - 1u) >> 1);
+  q.zero_point_product = (int32_t) (0u - (a_multiplier * (uint32_t) a_zero_point + b_multiplier * (uint32_t) b_zero_point));
+  q.y_zero_point = sum_zero_point, q.y_min = sum_min, q.y_max = sum_max;
+  *add_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_add_nc_q8(qnnp_operator_t op, size_t batch_size, const uint8_t* a, size_t a_stride,
+                                                  const uint8_t* b, size_t b_stride, uint8_t* sum, size_t sum_stride) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr || op->kind != kKindAdd) return qnnp_status_invalid_parameter;
+  op->input2 = b, op->in2_stride = b_stride;
+  return setup_nc(op, batch_size, a, a_stride, sum, sum_stride);
+}
+
+// ---- global average pooling (src/global-average-pooling.c:22-147) ---------------------------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_global_average_pooling_nwc_q8(size_t channels, uint8_t input_zero_point, float input_scale,
+                                                                       uint8_t output_zero_point, float output_scale,
+                                                                       uint8_t output_min, uint8_t output_max, uint32_t flags,
+                                                                       qnnp_operator_t* global_average_pooling_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_global_average_pooling_nwc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (channels == 0 || !scale_ok(input_scale) || !scale_ok(output_scale)) {
+    log_error("failed to create global average pooling operator: channels must be non-zero, scales finite and positive");
+    return qnnp_status_invalid_parameter;
+  }
+  const float input_output_scale = input_scale / output_scale;
+  if (input_output_scale < 0x1.0p-8f || input_output_scale >= 0x1.0p+8f) {
+    log_error("failed to create global average pooling operator with %.7g input-to-output scale ratio: must be in [2**-8, 2**8)",
+              input_output_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  qnnp_operator* op = new_operator(kKindGavgPool);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->channels = channels;
+  op->izp = input_zero_point, op->ozp = output_zero_point, op->omin = output_min, op->omax = output_max;
+  op->in_scale = input_scale, op->out_scale = output_scale;
+  *global_average_pooling_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_global_average_pooling_nwc_q8(qnnp_operator_t op, size_t batch_size, size_t width,
+                                                                      const uint8_t* input, size_t input_stride, uint8_t* output,
+                                                                      size_t output_stride) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr || op->kind != kKindGavgPool) return qnnp_status_invalid_parameter;
+  if (batch_size == 0) {
+    op->batch = 0;
+    if (op->plan != nullptr) op->plan->valid = false;
+    return qnnp_status_success;
+  }
+  if (width == 0) {
+    log_error("failed to setup global average pooling operator with width %zu: width must be non-zero", width);
+    return qnnp_status_invalid_parameter;
+  }
+  op->batch = batch_size, op->in_w = width, op->in_h = 1;
+  op->input = input, op->in_stride = input_stride;
+  op->output = output, op->out_stride = output_stride;
+  // src/global-average-pooling.c:135-141: scale = input_scale / (output_scale * width), fp32 in this order
+  op->avgq = make_avg_quant(op->in_scale / (op->out_scale * (float) width), op->ozp, op->omin, op->omax);
+  return finish_setup(op, batch_size * width, op->channels, batch_size, op->channels);
+}
+
+// ---- average / max pooling (src/average-pooling.c:36-290, src/max-pooling.c:36-228) --------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_average_pooling2d_nhwc_q8(
+    uint32_t input_padding_top, uint32_t input_padding_right, uint32_t input_padding_bottom, uint32_t input_padding_left,
+    uint32_t pooling_height, uint32_t pooling_width, uint32_t stride_height, uint32_t stride_width, size_t channels,
+    uint8_t input_zero_point, float input_scale, uint8_t output_zero_point, float output_scale, uint8_t output_min,
+    uint8_t output_max, uint32_t flags, qnnp_operator_t* average_pooling_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_average_pooling2d_nhwc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  const uint32_t pooling_size = pooling_height * pooling_width;
+  if (pooling_size == 0 || pooling_size == 1 || stride_height == 0 || stride_width == 0 || channels == 0 ||
+      !scale_ok(input_scale) || !scale_ok(output_scale)) {  // src/average-pooling.c:66-113 (1x1 pooling is rejected there too)
+    log_error("failed to create average pooling with %ux%u pooling, %ux%u stride, %zu channels", pooling_width, pooling_height,
+              stride_width, stride_height, channels);
+    return qnnp_status_invalid_parameter;
+  }
+  const float input_output_scale = input_scale / output_scale;
+  if (input_output_scale < 0x1.0p-8f || input_output_scale >= 0x1.0p+8f || pooling_size >= 16777216) {
+    log_error("failed to create average pooling: scale ratio %.7g must be in [2**-8, 2**8), pooling size below 2**24",
+              input_output_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  qnnp_operator* op = new_operator(kKindAvgPool);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->pad_top = input_padding_top, op->pad_right = input_padding_right;
+  op->pad_bottom = input_padding_bottom, op->pad_left = input_padding_left;
+  op->kh = pooling_height, op->kw = pooling_width, op->stride_h = stride_height, op->stride_w = stride_width;
+  op->channels = channels;
+  op->izp = input_zero_point, op->omin = output_min, op->omax = output_max, op->ozp = output_zero_point;
+  // src/average-pooling.c:158-163: scale = input_scale / (output_scale * pooling_size); padded taps count (they read izp)
+  op->avgq = make_avg_quant(input_scale / (output_scale * (float) pooling_size), output_zero_point, output_min, output_max);
+  *average_pooling_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_create_max_pooling2d_nhwc_u8(
+    uint32_t input_padding_top, uint32_t input_padding_right, uint32_t input_padding_bottom, uint32_t input_padding_left,
+    uint32_t pooling_height, uint32_t pooling_width, uint32_t stride_height, uint32_t stride_width, uint32_t dilation_height,
+    uint32_t dilation_width, size_t channels, uint8_t output_min, uint8_t output_max, uint32_t flags,
+    qnnp_operator_t* max_pooling_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_max_pooling2d_nhwc_u8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  const uint32_t pooling_size = pooling_height * pooling_width;
+  if (pooling_size == 0 || pooling_size == 1 || stride_height == 0 || stride_width == 0 || dilation_height == 0 ||
+      dilation_width == 0 || channels == 0) {  // src/max-pooling.c:64-105
+    log_error("failed to create max pooling with %ux%u pooling, %ux%u stride, %ux%u dilation, %zu channels", pooling_width,
+              pooling_height, stride_width, stride_height, dilation_width, dilation_height, channels);
+    return qnnp_status_invalid_parameter;
+  }
+  qnnp_operator* op = new_operator(kKindMaxPool);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->pad_top = input_padding_top, op->pad_right = input_padding_right;
+  op->pad_bottom = input_padding_bottom, op->pad_left = input_padding_left;
+  op->kh = pooling_height, op->kw = pooling_width, op->stride_h = stride_height, op->stride_w = stride_width;
+  op->dil_h = dilation_height, op->dil_w = dilation_width;
+  op->channels = channels;
+  op->omin = output_min, op->omax = output_max;
+  *max_pooling_out = op;
+  return qnnp_status_success;
+}
+
+namespace {
+enum qnnp_status setup_pool2d(qnnp_operator* op, KernelKind kind, size_t batch_size, size_t input_height, size_t input_width,
+                              const uint8_t* input, size_t input_stride, uint8_t* output, size_t output_stride) {
+  if (!g_lib.initialized) return qnnp_status_uninitialized;
+  if (op == nullptr || op->kind != kind) return qnnp_status_invalid_parameter;
+  if (batch_size == 0) {
+    op->batch = 0;
+    if (op->plan != nullptr) op->plan->valid = false;
+    return qnnp_status_success;
+  }
+  if (input_width == 0 || input_height == 0) {
+    log_error("failed to setup pooling with %zux%zu input: input dimensions must be non-zero", input_width, input_height);
+    return qnnp_status_invalid_parameter;
+  }
+  op->batch = batch_size, op->in_h = input_height, op->in_w = input_width;
+  op->input = input, op->in_stride = input_stride;
+  op->out_h = output_dimension(op->pad_top + input_height + op->pad_bottom, op->kh, op->dil_h, op->stride_h);
+  op->out_w = output_dimension(op->pad_left + input_width + op->pad_right, op->kw, op->dil_w, op->stride_w);
+  op->output = output, op->out_stride = output_stride;
+  return finish_setup(op, batch_size * input_height * input_width, op->channels, batch_size * op->out_h * op->out_w, op->channels);
+}
+}  // namespace
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_average_pooling2d_nhwc_q8(qnnp_operator_t op, size_t batch_size, size_t input_height,
+                                                                  size_t input_width, const uint8_t* input, size_t input_stride,
+                                                                  uint8_t* output, size_t output_stride, pthreadpool_t threadpool) {
+  (void) threadpool;
+  return setup_pool2d(op, kKindAvgPool, batch_size, input_height, input_width, input, input_stride, output, output_stride);
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_max_pooling2d_nhwc_u8(qnnp_operator_t op, size_t batch_size, size_t input_height,
+                                                              size_t input_width, const uint8_t* input, size_t input_stride,
+                                                              uint8_t* output, size_t output_stride, pthreadpool_t threadpool) {
+  (void) threadpool;
+  return setup_pool2d(op, kKindMaxPool, batch_size, input_height, input_width, input, input_stride, output, output_stride);
+}
+
+// ---- channel shuffle (src/channel-shuffle.c) --------------------------------------------------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_channel_shuffle_nc_x8(size_t groups, size_t group_channels, uint32_t flags,
+                                                               qnnp_operator_t* channel_shuffle_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_channel_shuffle_nc_x8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (groups <= 1 || group_channels == 0) {
+    log_error("failed to create channel shuffle operator with %zu groups of %zu channels", groups, group_channels);
+    return qnnp_status_invalid_parameter;
+  }
+  qnnp_operator* op = new_operator(kKindShuffle);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->groups = (uint32_t) groups, op->gic = group_channels;
+  op->channels = groups * group_channels;
+  *channel_shuffle_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_channel_shuffle_nc_x8(qnnp_operator_t op, size_t batch_size, const uint8_t* input,
+                                                              size_t input_stride, uint8_t* output, size_t output_stride) {
+  if (op == nullptr || op->kind != kKindShuffle) return g_lib.initialized ? qnnp_status_invalid_parameter : qnnp_status_uninitialized;
+  return setup_nc(op, batch_size, input, input_stride, output, output_stride);
+}
+
+// ---- clamp (src/clamp.c) --------------------------------------------------------------------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_clamp_nc_u8(size_t channels, uint8_t output_min, uint8_t output_max, uint32_t flags,
+                                                     qnnp_operator_t* clamp_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_clamp_nc_u8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (channels == 0 || output_min > output_max) {
+    log_error("failed to create Clamp operator with %zu channels and [%u, %u] output range", channels, output_min, output_max);
+    return qnnp_status_invalid_parameter;
+  }
+  qnnp_operator* op = new_operator(kKindClamp);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->channels = channels, op->omin = output_min, op->omax = output_max;
+  *clamp_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_clamp_nc_u8(qnnp_operator_t op, size_t batch_size, const uint8_t* input,
+                                                    size_t input_stride, uint8_t* output, size_t output_stride) {
+  if (op == nullptr || op->kind != kKindClamp) return g_lib.initialized ? qnnp_status_invalid_parameter : qnnp_status_uninitialized;
+  return setup_nc(op, batch_size, input, input_stride, output, output_stride);
+}
+
+// ---- sigmoid / leaky ReLU: 256-entry tables built exactly as the reference builds them (src/sigmoid.c:96-112,
+//      src/leaky-relu.c:110-125), applied by the lookup kernel (src/x8lut/scalar.c) ---------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_sigmoid_nc_q8(size_t channels, uint8_t input_zero_point, float input_scale,
+                                                       uint8_t output_zero_point, float output_scale, uint8_t output_min,
+                                                       uint8_t output_max, uint32_t flags, qnnp_operator_t* sigmoid_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_sigmoid_nc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (channels == 0 || !scale_ok(input_scale) || !scale_ok(output_scale) || output_min >= output_max) {
+    log_error("failed to create Sigmoid operator: channels must be non-zero, scales finite and positive, min below max");
+    return qnnp_status_invalid_parameter;
+  }
+  if (output_scale != 0x1.0p-8f || output_zero_point != 0) {
+    log_error("failed to create Sigmoid operator: only output scale 1/256 and output zero point 0 are supported");
+    return qnnp_status_unsupported_parameter;
+  }
+  uint8_t table[256];
+  const float scaled_min = (float) (int32_t) output_min, scaled_max = (float) (int32_t) output_max;
+  for (int32_t i = 0; i < 256; i++) {
+    const float x = input_scale * (float) (i - (int32_t) (uint32_t) input_zero_point);
+    float scaled_sigmoid_x = 256.0f / (1.0f + expf(-x));
+    if (scaled_sigmoid_x < scaled_min) scaled_sigmoid_x = scaled_min;
+    if (scaled_sigmoid_x > scaled_max) scaled_sigmoid_x = scaled_max;
+    table[(uint32_t) i] = (uint8_t) lrintf(scaled_sigmoid_x);
+  }
+  bind_device();
+  qnnp_operator* op = new_operator(kKindLut);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->channels = channels;
+  const enum qnnp_status st = upload((void**) &op->d_lut, table, sizeof table);
+  if (st != qnnp_status_success) {
+    free_operator(op);
+    return st;
+  }
+  *sigmoid_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_sigmoid_nc_q8(qnnp_operator_t op, size_t batch_size, const uint8_t* input,
+                                                      size_t input_stride, uint8_t* output, size_t output_stride) {
+  if (op == nullptr || op->kind != kKindLut) return g_lib.initialized ? qnnp_status_invalid_parameter : qnnp_status_uninitialized;
+  return setup_nc(op, batch_size, input, input_stride, output, output_stride);
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_create_leaky_relu_nc_q8(size_t channels, float negative_slope, uint8_t input_zero_point,
+                                                          float input_scale, uint8_t output_zero_point, float output_scale,
+                                                          uint8_t output_min, uint8_t output_max, uint32_t flags,
+                                                          qnnp_operator_t* leaky_relu_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_leaky_relu_nc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  // src/leaky-relu.c:38-76
+  if (channels == 0 || negative_slope <= 0.0f || !isnormal(negative_slope) || negative_slope > 1.0f || !scale_ok(input_scale) ||
+      !scale_ok(output_scale) || output_min >= output_max) {
+    log_error("failed to create Leaky ReLU operator: invalid channels, slope, scales or output range");
+    return qnnp_status_invalid_parameter;
+  }
+  const float input_output_scale = input_scale / output_scale;
+  if (input_output_scale < 0x1.0p-8f || input_output_scale >= 0x1.0p+8f) {
+    log_error("failed to create Leaky ReLU operator with %.7g input-to-output scale ratio: must be in [2**-8, 2**8)",
+              input_output_scale);
+    return qnnp_status_unsupported_parameter;
+  }
+  uint8_t table[256];
+  const float scaled_min_less_zero_point = (float) ((int32_t) output_min - (int32_t) output_zero_point);
+  const float scaled_max_less_zero_point = (float) ((int32_t) output_max - (int32_t) output_zero_point);
+  for (int32_t i = 0; i < 256; i++) {
+    const float x = input_output_scale * (float) (i - (int32_t) (uint32_t) input_zero_point);
+    float y = x < 0.0f ? x * negative_slope : x;
+    if (y < scaled_min_less_zero_point) y = scaled_min_less_zero_point;
+    if (y > scaled_max_less_zero_point) y = scaled_max_less_zero_point;
+    table[(uint32_t) i] = (uint8_t) (lrintf(y) + (long) output_zero_point);
+  }
+  bind_device();
+  qnnp_operator* op = new_operator(kKindLut);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->channels = channels;
+  const enum qnnp_status st = upload((void**) &op->d_lut, table, sizeof table);
+  if (st != qnnp_status_success) {
+    free_operator(op);
+    return st;
+  }
+  *leaky_relu_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_leaky_relu_nc_q8(qnnp_operator_t op, size_t batch_size, const uint8_t* input,
+                                                         size_t input_stride, uint8_t* output, size_t output_stride) {
+  if (op == nullptr || op->kind != kKindLut) return g_lib.initialized ? qnnp_status_invalid_parameter : qnnp_status_uninitialized;
+  return setup_nc(op, batch_size, input, input_stride, output, output_stride);
+}
+
+// ---- softargmax (src/softargmax.c; run: src/operator-run.c:625-637) -------------------------------------------------------
+QNNP_EXPORT enum qnnp_status qnnp_create_softargmax_nc_q8(size_t channels, float input_scale, uint8_t output_zero_point,
+                                                          float output_scale, uint32_t flags, qnnp_operator_t* softargmax_out) {
+  (void) flags;
+  if (!g_lib.initialized) {
+    log_error("qnnp_create_softargmax_nc_q8 failed because QNNPACK is not properly initialized");
+    return qnnp_status_uninitialized;
+  }
+  if (channels == 0 || !scale_ok(input_scale) || !scale_ok(output_scale)) {
+    log_error("failed to create Soft ArgMax operator: channels must be non-zero, scales finite and positive");
+    return qnnp_status_invalid_parameter;
+  }
+  if (output_scale != 0x1.0p-8f || output_zero_point != 0) {
+    log_error("failed to create Soft ArgMax operator: only output scale 1/256 and output zero point 0 are supported");
+    return qnnp_status_unsupported_parameter;
+  }
+  // 256 entries as the reference builds them (src/softargmax.c:79-83); a row uses table + (255 - max), i.e. indices up to
+  // 510 — entries beyond 255 are never reached because x <= max, they are zero here for definiteness
+  uint32_t table[511] = {0};
+  const double qscale = fmin(((double) UINT32_MAX) / (double) channels, 8388607.0);
+  for (int32_t i = 0; i < 256; i++) {
+    const double scaled_exp_xi = qscale * exp((double) (i - 255) * (double) input_scale);
+    table[(uint32_t) i] = (uint32_t) lrint(scaled_exp_xi);
+  }
+  bind_device();
+  qnnp_operator* op = new_operator(kKindSoftargmax);
+  if (op == nullptr) return qnnp_status_out_of_memory;
+  op->channels = channels;
+  const enum qnnp_status st = upload((void**) &op->d_table32, table, sizeof table);
+  if (st != qnnp_status_success) {
+    free_operator(op);
+    return st;
+  }
+  *softargmax_out = op;
+  return qnnp_status_success;
+}
+
+QNNP_EXPORT enum qnnp_status qnnp_setup_softargmax_nc_q8(qnnp_operator_t op, size_t batch_size, const uint8_t* input,
+                                                         size_t input_stride, uint8_t* output, size_t output_stride) {
+  if (op == nullptr || op->kind != kKindSoftargmax)
+    return g_lib.initialized ? qnnp_status_invalid_parameter : qnnp_status_uninitialized;
+  return setup_nc(op, batch_size, input, input_stride, output, output_stride);
+}
