@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip int8 peak / tensor-bound GEMM / latency / host-pointer runs")
     return ap.parse_args()
 
 
@@ -95,8 +96,8 @@ def run_reference_stack(steps, warmup, batch, threads):
 def reference_main(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    batch = args.cpu_batch or 2 * threads
+    threads = usable_threads()
+    batch = args.cpu_batch or max(16, 2 * threads)
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
     ips, sec = run_reference_stack(steps, warmup, batch, threads)
     line = {
@@ -104,7 +105,7 @@ def reference_main(args, rank, world):
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "MobileNetV2-int8 conv stack, 53 operators (BASELINE.json configs[4]; bounded CPU sample)",
-                   "batch_per_step": batch, "threads": threads},
+                   "batch_per_step": batch, "threads": threads, "host": host_info()},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "reference",
                          "sample": f"{steps} passes of the full 53-operator stack over {batch} images, "
                                    f"unmodified reference (SSE2 ukernels) via oracle/_ref with a {threads}-thread pthreadpool"},
@@ -158,6 +159,144 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+
+def host_info():
+    """CPU model, cgroup CPU quota and usable cores of the box (explains the reference arm's box-to-box spread)."""
+    info = {"os_cpu_count": os.cpu_count()}
+    try:
+        info["sched_affinity"] = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["model"] = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_" + os.path.basename(path)] = open(path).read().strip()
+        except OSError:
+            pass
+    return info
+
+
+def usable_threads():
+    """Threads the reference arm should use: the cgroup's CPU share when one is set, else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def measure_tensor_bound_gemm(lib, torch, dev, peak_tops, m=65536, n=4096, k=4096, reps=5):
+    """BASELINE.json metric 1 where the tensor pipe can bind: q8gemm through qnnp_fully_connected_nc_q8 at
+    M = 65536, N = K = 4096 (arithmetic intensity 2MNK / (MK + NK + MN) = 3.9 k ops/byte, far above the ridge), device
+    pointers, CUDA events; a few output rows are checked bit for bit against the C oracle."""
+    import numpy as np
+    from oracle import q8_oracle as O
+    rng = np.random.default_rng(5)
+    w = rng.integers(0, 256, (n, k), dtype=np.uint8)
+    b = rng.integers(-10000, 10000, (n,), dtype=np.int32)
+    kw = dict(izp=127, input_scale=1.0, kzp=127, kernel_scale=float(np.float32(1.0 / (128.0 * k ** 0.5))), ozp=127, output_scale=1.0)
+    st, op = lib.create_fully_connected(w, b, **kw)
+    if st != 0:
+        return {"error": f"create status {st}"}
+    x = torch.randint(0, 256, (m * k,), dtype=torch.uint8, device=dev)
+    y = torch.empty(m * n, dtype=torch.uint8, device=dev)
+    assert lib.setup_fully_connected(op, m, x.data_ptr(), k, y.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    for _ in range(2):
+        assert lib.run_async(op) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream()
+    e0.record(stream)
+    for _ in range(reps):
+        assert lib.run_async(op) == 0
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    rows = [0, 1, m // 2 - 1, m - 1]
+    xr = np.stack([x[r * k:(r + 1) * k].cpu().numpy() for r in rows])
+    want = O.COracle().fully_connected(xr, w, b, **kw)
+    got = np.stack([y[r * n:(r + 1) * n].cpu().numpy() for r in rows])
+    lib.delete(op)
+    tops = 2.0 * m * n * k / ms / 1e9
+    return {"m": m, "n": n, "k": k, "ms": ms, "tops": tops, "frac": tops / peak_tops if peak_tops else None,
+            "rows_checked": rows, "mismatches": int(np.count_nonzero(got != want))}
+
+
+def measure_small_batch_latency(lib, torch, dev, M, params, batches=(1, 32), iters=50):
+    """QNNPACK's own regime: one or a few images.  The 53 asynchronous C-ABI runs of a step are captured once in a CUDA
+    graph (launch-bound: ~53 kernels of a few microseconds each) and replayed; the un-captured loop is timed beside it."""
+    out = {}
+    for b in batches:
+        stack = M.Stack(lib, seed=0, params=params)
+        cap = stack.max_activation_bytes(b)
+        x = torch.randint(0, 256, (b * 224 * 224 * 3,), dtype=torch.uint8, device=dev)
+        a_, b_ = torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(cap, dtype=torch.uint8, device=dev)
+        stack.setup(b, a_.data_ptr(), b_.data_ptr(), first_input=x.data_ptr())
+        stream = torch.cuda.current_stream()
+        for _ in range(3):
+            stack.run(asynchronous=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(iters):
+            stack.run(asynchronous=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / iters
+        eager_ms = e0.elapsed_time(e1) / iters
+        entry = {"eager_ms": eager_ms, "eager_host_us_per_launch": wall * 1e6 / len(stack.ops)}
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                stack.run(asynchronous=True)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(iters):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            entry["graph_ms"] = e0.elapsed_time(e1) / iters
+            entry["images_per_s_graph"] = b / (entry["graph_ms"] * 1e-3)
+        except Exception as exc:  # graph capture is an optimisation of the caller, not of the library
+            entry["graph_error"] = str(exc)[:200]
+        out[f"batch_{b}"] = entry
+        stack.delete()
+    return out
+
+
+def measure_e2e_plugin(lib, M, params, batch=64, steps=3):
+    """The stock caller's path (reference bench/convolution.cc:83-97 loop): qnnp_setup_* with HOST pointers and a
+    synchronous qnnp_run_operator per layer — every layer's input and output cross PCIe inside the call."""
+    import numpy as np
+    stack = M.Stack(lib, seed=0, params=params)
+    cap = stack.max_activation_bytes(batch) + 64
+    x = np.random.default_rng(1).integers(0, 256, batch * 224 * 224 * 3 + 64, dtype=np.uint8)
+    a, b = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    stack.setup(batch, a[16:], b[16:], first_input=x[16:])
+    stack.run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        stack.run()
+    dt = (time.perf_counter() - t0) / steps
+    stack.delete()
+    moved = sum(l.in_elems_per_image + l.out_elems_per_image for l in stack.layers) * batch
+    return {"value": batch / dt, "unit": "images/s", "batch": batch, "ms_per_step": dt * 1e3, "pcie_bytes_per_step": int(moved),
+            "note": "host pointers, synchronous qnnp_run_operator per layer (pageable memory): every activation crosses "
+                    "PCIe twice; device pointers + qnnp_cuda_run_operator_async is the intended integration (e2e above)"}
 
 
 def b200_main(args, rank, local_rank, world):
@@ -310,6 +449,20 @@ def b200_main(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
+    # ---- side measurements (rank 0, outside every timed region) ---------------------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        try:
+            tops, ms = lib.measure_int8_peak(20000, 3)
+            extras["int8_peak"] = {"tops": tops, "ms_per_launch": ms, "how": "qnnp_cuda_measure_int8_peak: smem-resident tcgen05.mma "
+                                   "kind::i8 loop, 148 CTAs x 160000 UMMAs of 128x256x32 (q8_peak_sm100.cu)"}
+            extras["tensor_bound_gemm"] = measure_tensor_bound_gemm(lib, torch, dev, tops)
+            if world == 1:
+                extras["small_batch_latency"] = measure_small_batch_latency(lib, torch, dev, M, params)
+                extras["e2e_plugin_host_pointers"] = measure_e2e_plugin(lib, M, params)
+        except Exception as exc:
+            extras["error"] = str(exc)[:300]
+
     # ---- reporting (rank 0) -----------------------------------------------------------------------------
     peak_gbs, peak_src = measured_peaks()
     kinds = {"igemm": ("conv", "pw", "fc"), "dwconv3x3": ("dw",)}
@@ -351,20 +504,31 @@ def b200_main(args, rank, local_rank, world):
             sweep_rows.append({"layer": l.name, "m": B * l.out_h * l.out_h if l.kind != "fc" else B, "n": l.cout, "k": l.cin,
                                "ms": layer_ms[i], "tops": l.ops(B) / 1e9 / layer_ms[i],
                                "gbs": l.algorithmic_bytes(B) / 1e6 / layer_ms[i], "frac_of_roofline": bound_ms / layer_ms[i]})
+    int8_peak = (extras.get("int8_peak") or {}).get("tops")
     q8gemm = {"tops": sw_ops / 1e9 / sw_ms, "pct_of_int8_peak_nominal": 100.0 * sw_ops / 1e9 / sw_ms / INT8_PEAK_TOPS_NOMINAL,
-              "int8_peak_tops_nominal": INT8_PEAK_TOPS_NOMINAL, "shapes": sweep_rows}
+              "int8_peak_tops_nominal": INT8_PEAK_TOPS_NOMINAL, "int8_peak_tops_measured": int8_peak,
+              "pct_of_int8_peak_measured": (100.0 * sw_ops / 1e9 / sw_ms / int8_peak) if int8_peak else None,
+              "tensor_bound": extras.get("tensor_bound_gemm"), "shapes": sweep_rows,
+              "note": "every MobileNetV2 shape is HBM-bound (frac_of_roofline per shape); tensor_bound is the GEMM where the "
+                      "int8 tensor pipe can bind"}
     layers_out = [{"layer": l.name, "kind": l.kind, "ms": layer_ms[i], "gbs": l.algorithmic_bytes(B) / 1e6 / layer_ms[i],
                    "tops": l.ops(B) / 1e9 / layer_ms[i]} for i, l in enumerate(stack.layers)]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            threads = os.cpu_count() or 1
-            cb = args.cpu_batch or 2 * threads
+            threads = usable_threads()
+            cb = args.cpu_batch or max(16, 2 * threads)
             ips, sec = run_reference_stack(3, 1, cb, threads)
+            scaling = {}
+            for t in sorted({1, max(1, threads // 4), threads}):
+                if t != threads:
+                    scaling[str(t)] = run_reference_stack(1, 1, max(4, min(cb, 2 * t)), t)[0]
+            scaling[str(threads)] = ips
             cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "reference",
                    "sample": f"3 passes of the full 53-operator stack over {cb} images, unmodified reference "
-                             f"(oracle/_ref, SSE2 ukernels) with a {threads}-thread pthreadpool"}
+                             f"(oracle/_ref, SSE2 ukernels) with a {threads}-thread pthreadpool",
+                   "thread_scaling_images_per_s": scaling, "host": host_info()}
         except Exception as exc:  # the baseline is informative; never let it take the GPU numbers down
             cpu = {"value": None, "unit": "images/s", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
 
@@ -378,7 +542,7 @@ def b200_main(args, rank, local_rank, world):
                    "l2": "every layer streams activations far larger than the 126 MB L2 (no flush needed)",
                    "quantization": "zero points 127, requant scale 1/(128*sqrt(K)), clamp 0..255",
                    "weights_broadcast_bytes": bcast_bytes},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity_check": parity, "extras": extras,
         "roofline": roofline, "cpu_baseline": cpu, "q8gemm_sweep": q8gemm, "per_kernel": per_kernel, "layers": layers_out,
         "stack_ops_g": stack.total_ops(B) / 1e9, "stack_algorithmic_gb": stack.total_bytes(B) / 1e9,
         "stack_frac_of_hbm_roofline": (stack.total_bytes(B) / 1e6 / peak_gbs) / ms_per_step,

@@ -70,7 +70,8 @@ struct DwTcParams {
   int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
   int acc_stride, acc_stages;
   int epi_poll_ns;          // back-off of the epilogue warps' accumulator poll (0 = spin)
-  // item schedule: a CTA's next item is `grid` items further; in (cb, xtile, ytile, nblk) digits that is this step
+  // item schedule: a CTA's next item is the NEXT item; in (cb, xtile, ytile, nblk) digits that is this step
+  int chunk;                // items per CTA: CTA b runs items [b * chunk, min(total, (b + 1) * chunk))
   int step_cb, step_x, step_y, step_n;
   uint32_t inv_g, inv_tail; // ceil(2^16 / m) for m = mt and for the sub-tile count of the last x tile
   int rq_mode;

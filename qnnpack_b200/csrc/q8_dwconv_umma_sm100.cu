@@ -276,7 +276,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl.tmem_base;
-  const uint32_t first = blockIdx.x, step = gridDim.x, total = (uint32_t) p.total_items;
+  // Schedule: every CTA owns ONE CONTIGUOUS run of `chunk` items (channel block fastest, then x tile, y tile, image), not
+  // every grid-th item.  The channel blocks of a spatial tile — which share 32-byte sectors whenever a pixel's channel
+  // block is not sector-aligned (C = 144: every odd pixel) — and the row-halo neighbours are then read and written by the
+  // SAME SM within microseconds.  With the round-robin schedule those sector halves came from different CTAs whose skew
+  // grew over a launch; measured on b3_dw (C = 144, 56x56): 8.7 GB of DRAM traffic for 3.7 GB of tensors once the
+  // kernel's per-item time dropped (L2 hit rate 41 %), against 4.8 GB before.
+  const uint32_t first = blockIdx.x * (uint32_t) p.chunk, step = 1u;
+  const uint32_t total = min((uint32_t) p.total_items, first + (uint32_t) p.chunk);
 
   if (warp == kTmaWarp) {
     // ===================================== TMA producer =====================================

@@ -1092,6 +1092,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         const Item it = decode_item(p, item);
         mbar_wait_relaxed(smem_u32(&ctl.out_full[pair]), k & 1, 20);
         const int rows = it.mt_eff * kTileM;
+        if (p.e2_dense) {  // contiguous output rows: the whole item is one run of bytes
+          const long long left = p.M - it.m0;
+          const uint32_t valid = left < rows ? (uint32_t) left : (uint32_t) rows;
+          bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, valid * (uint32_t) p.goc);
+        }
         for (int pk = 0; pk < p.e2_panels; pk++) {
           const int col = it.nt * p.n_tile + p.e2_col0[pk];
           if (col >= p.goc) break;

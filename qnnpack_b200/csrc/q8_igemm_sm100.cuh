@@ -69,6 +69,8 @@ struct IgemmParams {
   // out_mode 2 ("panel" epilogue): the pair's staging image is a set of column panels [panel][sub-tile*128 + row][width],
   // width in {128, 64, 32, 16} bytes with the matching TMA swizzle (conflict-free 16-byte staging stores for every
   // pitch), written to global memory by 2-D tensor stores that clip rows >= M and columns >= N themselves.
+  int e2_dense;               // 1: one dense [row][N] image + ONE 1-D bulk store per item instead of panels — used when the
+                              //    output rows are contiguous (stride == N) and the pitch N is conflict-free (N / 16 odd)
   int e2_panels;              // panels per n-tile (greedy split of n_tile into 128/64/32/16)
   int e2_box_rows;            // rows per tensor store: 256 when mt is even, else 128
   int e2_col0[4];             // first column of panel k inside the n-tile

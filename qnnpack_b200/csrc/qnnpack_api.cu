@@ -811,8 +811,17 @@ enum PlanPath {
 bool env_set(const char* name) { return getenv(name) != nullptr; }
 
 // Panel epilogue tables (q8_igemm_sm100.cuh: out_mode 2): n_tile is split greedily into panels of 128/64/32/16 bytes.
-void fill_panel_tables(q8::IgemmParams& p) {
+void fill_panel_tables(q8::IgemmParams& p, bool dense) {
   const int W = p.folded ? 32 : 16;
+  if (dense) {  // one dense image of pitch N = n_tile: unit c starts at byte c * W of its row, no swizzle
+    p.e2_dense = 1, p.e2_panels = 0, p.e2_box_rows = 128;
+    for (int c = 0; c < (p.n_tile + W - 1) / W && c < 16; c++) {
+      p.e2_unit[c].x = (uint32_t) (c * W);
+      p.e2_unit[c].y = (uint32_t) p.n_tile;  // pitch; lsh = mask = 0
+    }
+    return;
+  }
+  p.e2_dense = 0;
   int col = 0, off = 0, k = 0;
   const int widths[4] = {128, 64, 32, 16};
   for (int wi = 0; wi < 4; wi++) {
@@ -940,7 +949,12 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       pl.has_smaps = false;
       if ((op->rq_mode == 5 || op->rq_mode == 6) && op->groups == 1 && ((uintptr_t) out % 16) == 0 && (op->out_stride % 16) == 0 &&
           g_lib.dbg_acc == nullptr && !env_set("QNNP_CUDA_NO_PANEL_STORE")) {
-        fill_panel_tables(p);
+        // narrow dense outputs whose pitch is conflict-free (N / 16 odd: the 8 lanes of a store phase hit 8 different
+        // 16-byte bank groups) leave as ONE contiguous bulk copy per item — measured: 16-byte-wide tensor-store boxes
+        // cost the N = 16 projection 13 % (0.70 vs 0.62 ms)
+        const bool dense = op->n_tiles == 1 && op->out_stride == op->goc && (int) op->goc == op->n_tile && ((op->goc / 16) & 1) == 1 &&
+            op->goc <= 112 && !env_set("QNNP_CUDA_NO_DENSE_STORE");
+        fill_panel_tables(p, dense);
         bool ok = true;
         bool done[4] = {false, false, false, false};
         for (int k = 0; k < p.e2_panels && ok; k++) {
@@ -1034,9 +1048,11 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
         tp.out_stride = (long long) op->out_stride;
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
         if (const char* ev = getenv("QNNP_CUDA_DW_POLL_NS")) tp.epi_poll_ns = atoi(ev);
-        const long long grid = persistent_grid(tp.total_items);
-        {  // digits of the grid size in the item schedule's mixed radix (cb fastest), and the unit-split reciprocals
-          long long r = grid;
+        long long grid = persistent_grid(tp.total_items);
+        tp.chunk = (int) ((tp.total_items + grid - 1) / grid);         // contiguous run of items per CTA
+        grid = (tp.total_items + tp.chunk - 1) / tp.chunk;             // (CTAs that would start beyond the end are not launched)
+        {  // digits of the per-item step (1) in the item schedule's mixed radix (cb fastest), and the unit-split reciprocals
+          long long r = 1;
           tp.step_cb = (int) (r % tp.cblocks), r /= tp.cblocks;
           tp.step_x = (int) (r % tp.xt), r /= tp.xt;
           tp.step_y = (int) (r % tp.yt), r /= tp.yt;
@@ -1559,7 +1575,7 @@ QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, 
 QNNP_EXPORT void qnnp_cuda_debug_panel_tables(int n_tile, int mt, int folded, int out[50]) {
   q8::IgemmParams p{};
   p.n_tile = n_tile, p.mt = mt, p.folded = folded;
-  fill_panel_tables(p);
+  fill_panel_tables(p, false);
   out[0] = p.e2_panels, out[1] = p.e2_box_rows;
   for (int k = 0; k < 4; k++) out[2 + 4 * k] = p.e2_col0[k], out[3 + 4 * k] = p.e2_width[k], out[4 + 4 * k] = p.e2_off[k], out[5 + 4 * k] = p.e2_map[k];
   for (int c = 0; c < 16; c++) out[18 + 2 * c] = (int) p.e2_unit[c].x, out[19 + 2 * c] = (int) p.e2_unit[c].y;
