@@ -278,6 +278,46 @@ def measure_small_batch_latency(lib, torch, dev, M, params, batches=(1, 32), ite
     return out
 
 
+def measure_full_network(lib, torch, dev, M, batch, steps, warmup, peak_gbs):
+    """The real MobileNetV2-int8 graph — the 52 convolutions of the headline stack plus the 10 residual adds, the global
+    average pool and the per-image classifier (64 qnnpack.h operators) — device-timed like the headline, then gated byte
+    for byte against the reference chain on sampled images."""
+    from oracle import chain_check as CC
+    layers = M.network()
+    params = [M.layer_params(l, i)[:2] for i, l in enumerate(layers)]
+    net = M.Network(lib, seed=0, params=params)
+    cap = net.max_activation_bytes(batch)
+    x = torch.randint(0, 256, (batch * 224 * 224 * 3,), dtype=torch.uint8, device=dev)
+    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(net.nbuf)]
+    net.setup(batch, [b.data_ptr() for b in bufs], x.data_ptr())
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        net.run(asynchronous=True)
+    torch.cuda.synchronize()
+    nl = len(layers)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(nl + 1)] for _ in range(steps)]
+    for s_ in range(steps):
+        ev[s_][0].record(stream)
+        net.run(asynchronous=True, hook=lambda i, after, s_=s_: ev[s_][i + 1].record(stream) if after else None)
+    torch.cuda.synchronize()
+    ms = ev[0][0].elapsed_time(ev[-1][nl]) / steps
+    layer_ms = [statistics.fmean(ev[s_][i].elapsed_time(ev[s_][i + 1]) for s_ in range(steps)) for i in range(nl)]
+    images = sorted({0, 1 % batch, max(0, batch // 2 - 1), batch - 1})
+    parity = CC.check_device_network(net, params, batch, x, bufs, images)
+    by_kind = {}
+    for l, t in zip(layers, layer_ms):
+        k = by_kind.setdefault(l.kind, {"launches": 0, "ms": 0.0, "gb": 0.0})
+        k["launches"] += 1
+        k["ms"] += t
+        k["gb"] += l.algorithmic_bytes(batch) / 1e9
+    for k in by_kind.values():
+        k["frac_of_hbm_peak"] = k["gb"] * 1e3 / k["ms"] / peak_gbs
+    net.delete()
+    return {"operators": nl, "batch": batch, "ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "buffers": net.nbuf,
+            "algorithmic_gb": net.total_bytes(batch) / 1e9, "by_kind": by_kind,
+            "parity_check": {k: parity[k] for k in ("images", "layers", "bytes_compared", "mismatches", "oracle")}}
+
+
 def measure_e2e_plugin(lib, M, params, batch=64, steps=3):
     """The stock caller's path (reference bench/convolution.cc:83-97 loop): qnnp_setup_* with HOST pointers and a
     synchronous qnnp_run_operator per layer — every layer's input and output cross PCIe inside the call."""
@@ -458,6 +498,7 @@ def b200_main(args, rank, local_rank, world):
                                    "kind::i8 loop, 148 CTAs x 160000 UMMAs of 128x256x32 (q8_peak_sm100.cu)"}
             extras["tensor_bound_gemm"] = measure_tensor_bound_gemm(lib, torch, dev, tops)
             if world == 1:
+                extras["full_network"] = measure_full_network(lib, torch, dev, M, B, min(args.steps, 5), 2, measured_peaks()[0])
                 extras["small_batch_latency"] = measure_small_batch_latency(lib, torch, dev, M, params)
                 extras["e2e_plugin_host_pointers"] = measure_e2e_plugin(lib, M, params)
         except Exception as exc:

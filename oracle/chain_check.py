@@ -28,7 +28,7 @@ def _host_lib():
 
 def _srcs(nodes, i):
     """Producers of node i's inputs (-1 = the network input).  The conv stack is a plain chain."""
-    return getattr(nodes[i], "srcs", None) or [i - 1]
+    return M.node_srcs(nodes, i)
 
 
 class ReferenceChain:
@@ -80,7 +80,7 @@ def check_graph(nodes, params, images, fetch_input, fetch_output, fetch_rows=Non
     try:
         x0 = np.stack([np.asarray(fetch_input(im), np.uint8).reshape(-1) for im in images])
         for i, node in enumerate(nodes):
-            if node.kind == "fc":
+            if node.kind == "fc" and node.rowwise:
                 # rows of the flat previous output, not images: checked in isolation on rows fetched from the device
                 rows = sorted({r for r in [0, 1, 48] + list(images) if r < n_rows})
                 xin = np.stack([fetch_rows(i, "in", r) for r in rows])
@@ -143,5 +143,28 @@ def check_device_stack(stack, params, batch, x_in, buf_a, buf_b, images, log=Non
                       fetch_input=lambda im: x_in[im * e0:(im + 1) * e0].cpu().numpy(),
                       fetch_output=lambda i, im: got[i][im],
                       fetch_rows=lambda i, which, r: rows[(i, which)][r], n_rows=batch, log=log)
+    res["batch"] = int(batch)
+    return res
+
+
+def check_device_network(net, params, batch, x_in, buffers, images, log=None):
+    """The same gate for the real MobileNetV2 graph (qnnpack_b200.mobilenet_v2.Network: residual adds, global average
+    pool, per-image classifier): `buffers` are the torch uint8 CUDA tensors the network was set up with."""
+    import torch
+
+    layers = net.layers
+    got = {}
+
+    def hook(i, after):
+        if after:
+            e = layers[i].out_elems_per_image
+            out = buffers[net.assign[i]]
+            got[i] = {im: out[im * e:(im + 1) * e].cpu().numpy() for im in images}
+
+    net.run(asynchronous=True, hook=hook)
+    torch.cuda.synchronize()
+    e0 = layers[0].in_elems_per_image
+    res = check_graph(layers, params, images, fetch_input=lambda im: x_in[im * e0:(im + 1) * e0].cpu().numpy(),
+                      fetch_output=lambda i, im: got[i][im], n_rows=batch, log=log)
     res["batch"] = int(batch)
     return res

@@ -228,8 +228,8 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t
       a16[i] = b16[i] + (uint32_t) j * 8;
       dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
     }
-    mbar_wait(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
-    mbar_wait(bar_full + 8u * (uint32_t) stage, phase);
+    mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
+    mbar_wait_parked(bar_full + 8u * (uint32_t) stage, phase);
     tc_fence_after_sync();
     if (elect_one()) {
       // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
@@ -339,18 +339,26 @@ __global__ void __launch_bounds__(kThreads, 1)
     int as = 0;
     uint32_t as_phase = 0;
     ItemPos pos = first_pos(p, first);
+    // values that depend on the SPATIAL tile only: with the contiguous schedule (channel block fastest) they change once
+    // every `cblocks` items, so they are recomputed only then
+    uint8_t* tile_base = nullptr;   // warp-uniform origin of the spatial tile in the output tensor (channel 0)
+    bool row_ok = false;
+    uint32_t rm_row = 0;            // row class * 8 * channels: index of this lane's row of bias_cls, column class 0
     for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
       const DwItem it = make_item(p, pos);
       const int c0 = it.cb * p.G * 16;
-      // warp-uniform origin of the item in the output tensor
-      uint8_t* const obase = p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w + it.ox0) * p.out_stride + c0;
-      const int oy = it.oy0 + oyl;
-      const bool row_ok = img < p.nb && it.n0 + img < p.batch && oy < p.out_h;
-      // row class: bit k set iff input row iy0 + k lies inside the image (taps below 0 / at or above in_h are padding)
-      const int iy0 = oy * S - p.pad_top;
-      const int rlo = iy0 < 0 ? -iy0 : 0, rhi = iy0 + 3 - p.in_h > 0 ? iy0 + 3 - p.in_h : 0;
-      const uint32_t rm = rhi >= 3 ? 0u : (((7u << rlo) & 7u) & (7u >> rhi));
-      const uint32_t bias_row = rm * 8u * (uint32_t) p.channels + (uint32_t) c0;  // index into bias_cls, column class 0
+      if (item == first || it.cb == 0) {
+        tile_base = p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w + it.ox0) * p.out_stride;
+        const int oy = it.oy0 + oyl;
+        row_ok = img < p.nb && it.n0 + img < p.batch && oy < p.out_h;
+        // row class: bit k set iff input row iy0 + k lies inside the image (taps below 0 / at or above in_h are padding)
+        const int iy0 = oy * S - p.pad_top;
+        const int rlo = iy0 < 0 ? -iy0 : 0, rhi = iy0 + 3 - p.in_h > 0 ? iy0 + 3 - p.in_h : 0;
+        const uint32_t rm = rhi >= 3 ? 0u : (((7u << rlo) & 7u) & (7u >> rhi));
+        rm_row = rm * 8u * (uint32_t) p.channels;
+      }
+      uint8_t* const obase = tile_base + c0;
+      const uint32_t bias_row = rm_row + (uint32_t) c0;
       const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
       mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
       tc_fence_after_sync();

@@ -676,11 +676,11 @@ __device__ __forceinline__ void epi2_requant16(const IgemmParams& p, const int32
     w[t] = pack_sat_u8x4(rq(v[4 * t], true), rq(v[4 * t + 1], false), rq(v[4 * t + 2], true), rq(v[4 * t + 3], false));
 }
 
-// One unit: W accumulator columns of the warp's 32 rows.  a0 = swizzled smem address of the unit's first 16-byte chunk in
-// this lane's staging row (the second chunk of a 32-column unit is a0 ^ 16: units start on 32-byte boundaries).
+// One unit: W accumulator columns of the warp's 32 rows.  a0 / a1 = smem addresses of the unit's first / second 16-byte
+// chunk in this lane's staging row.
 template <int RQ, int W, bool FOLDED>
 __device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, uint32_t rs_taddr, uint32_t bias_addr, uint32_t a0,
-                                          bool first, bool last, uint32_t tmem_empty_bar, uint32_t out_free_bar,
+                                          uint32_t a1, bool first, bool last, uint32_t tmem_empty_bar, uint32_t out_free_bar,
                                           uint32_t out_free_parity) {
   int32_t v[W];
   if constexpr (W == 32) {
@@ -713,7 +713,7 @@ __device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, 
   if (first) mbar_wait(out_free_bar, out_free_parity);  // the tensor stores of the pair's previous item have read staging
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
   if constexpr (W == 32)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0 ^ 16u), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
 // All units of one item for warp (quarter q, half): the two warps of a quarter take alternate units of the item's
@@ -742,12 +742,15 @@ __device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint
     const uint2 ent = p.e2_unit[c];
     const uint32_t pitch = ent.y & 0xFFu, lsh = (ent.y >> 8) & 0xFFu, mask = ent.y >> 16;
     const uint32_t a0 = (staging + ent.x + jrow * pitch) ^ ((row << lsh) & mask);
+    // second chunk of a 32-column unit: in a swizzled panel the unit starts on a 32-byte boundary of a 32-byte-multiple
+    // pitch, so the neighbouring chunk differs in address bit 4 only; the dense image has pitch N with N / 16 odd
+    const uint32_t a1 = p.e2_dense ? a0 + 16u : a0 ^ 16u;
     const uint32_t taddr = tsub + (uint32_t) (c * W);
     if (c < full) {
-      epi2_unit<RQ, W, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, first, last, tmem_empty_bar,
+      epi2_unit<RQ, W, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
                                out_free_bar, out_free_parity);
     } else {
-      epi2_unit<RQ, 16, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, first, last, tmem_empty_bar,
+      epi2_unit<RQ, 16, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
                                 out_free_bar, out_free_parity);
     }
     c += 2;
@@ -784,7 +787,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (tid == 0) {
     for (int s = 0; s < p.num_stages; s++) {
       // arrivals per stage: the 128 cp.async loaders, or one expect_tx arrival (TMA) plus the loaders when they stream B
-      mbar_init(smem_u32(&ctl.full[s]), VEC == kVecTma ? (p.b_resident ? 1 : 1 + kLoadThreads) : kLoadThreads);
+      // arrivals per stage: one expect_tx arrival when the TMA thread moves everything (A tiles and, when they stream,
+      // the weights), else the 128 cp.async loaders
+      mbar_init(smem_u32(&ctl.full[s]), VEC == kVecTma ? 1 : kLoadThreads);
       mbar_init(smem_u32(&ctl.empty[s]), kMmaWarps);  // one tcgen05.commit per issuing warp
     }
     for (int s = 0; s < kMaxAccStages; s++) {
@@ -861,17 +866,29 @@ __global__ void __launch_bounds__(kThreads, 1)
       const Item it = decode_item(p, item);
       for (int ks = 0; ks < p.k_stages; ks++) {
         if constexpr (VEC == kVecTma) {
-          if (p.b_resident && ltid != 0) continue;  // one thread drives the TMA; the others only matter when B streams
+          if (ltid != 0) continue;  // one thread drives the TMA (activations as tensor boxes, streamed weights as bulk copies)
         }
         mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
         const uint32_t a_stage = a_smem + stage * p.stage_bytes;
         if constexpr (VEC == kVecTma) {
           if (ltid == 0) {
             const uint32_t bar = smem_u32(&ctl.full[stage]);
-            mbar_arrive_expect_tx(bar, (uint32_t) (it.mt_eff * p.skc) * kChunkBytes);
+            // streamed weights: the stage's K chunks of this (group, n-tile) block are ONE contiguous run of the packed
+            // blob, moved by bulk copies on the same barrier (round 1 used 128 threads x cp.async for it: the large-GEMM
+            // and N >= 320 layers spent their time in those loader warps)
+            int cs = p.nkc - ks * p.skc;
+            cs = cs < p.skc ? cs : p.skc;
+            const uint32_t b_bytes = p.b_resident ? 0u : (uint32_t) (cs * p.n_mma) * 16u;
+            mbar_arrive_expect_tx(bar, (uint32_t) (it.mt_eff * p.skc) * kChunkBytes + b_bytes);
             for (int j = 0; j < it.mt_eff; j++)
               tma_load_3d(a_stage + (uint32_t) (j * p.skc) * kChunkBytes, &tmap_a, 0, (int) (it.m0 + (long long) j * kTileM),
                           ks * p.skc, bar);
+            if (!p.b_resident) {
+              const uint8_t* wsrc =
+                  p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.blk_chunks + (size_t) ks * p.skc) * p.n_mma * 16;
+              const uint32_t b_dst = a_stage + (uint32_t) (p.mt * p.skc) * kChunkBytes;
+              for (uint32_t o = 0; o < b_bytes; o += 16384) bulk_g2s(b_dst + o, wsrc + o, b_bytes - o < 16384 ? b_bytes - o : 16384u, bar);
+            }
           }
         } else if constexpr (MODE == kModeGemm) {
           load_a_gemm<VEC>(p, it, ks, a_stage, ltid);
@@ -891,16 +908,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else {
           load_a_conv<VEC>(p, it, ks, a_stage, ltid);
         }
-        if (!p.b_resident) {
+        if (VEC != kVecTma && !p.b_resident) {
           int cs = p.nkc - ks * p.skc;
           cs = cs < p.skc ? cs : p.skc;
           const uint8_t* wsrc =
               p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.blk_chunks + (size_t) ks * p.skc) * p.n_mma * 16;
           copy_bytes16(a_stage + p.mt * p.skc * kChunkBytes, wsrc, cs * p.n_mma * 16, ltid);
         }
-        if constexpr (VEC == kVecTma) {
-          if (!p.b_resident) cp_async_mbar_arrive_noinc(smem_u32(&ctl.full[stage]));
-        } else {
+        if constexpr (VEC != kVecTma) {
           fence_proxy_async_smem();  // st.shared fills (padding taps / byte path) -> UMMA reads
           cp_async_mbar_arrive_noinc(smem_u32(&ctl.full[stage]));
         }
@@ -948,13 +963,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         const Item it = decode_item(p, item);
         if (++as == p.acc_stages) as = 0;
         as_phase ^= (as == 0);
-        mbar_wait(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
+        mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_u + as * p.acc_stride;
         // base of this (group, n_tile)'s resident block: [B1: nkc][B2 full: 2][B2 tail: 2][bias digits: 2 per step]
         const uint32_t blk = b_smem_u + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.blk_chunks) * b_lbo;
         for (int ks = 0; ks < p.k_stages; ks++) {
-          mbar_wait(bar_full + 8u * (uint32_t) stage, phase);
+          mbar_wait_parked(bar_full + 8u * (uint32_t) stage, phase);
           fence_proxy_async_smem();
           tc_fence_after_sync();
           const uint32_t a_stage = a_smem_u + stage * p.stage_bytes;

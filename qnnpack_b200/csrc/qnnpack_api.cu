@@ -1574,8 +1574,8 @@ QNNP_EXPORT int qnnp_cuda_debug_plan_igemm(size_t k, size_t n, uint32_t groups, 
  * [2+4k..] col0, width, off, map of panel k (4 panels), [18+2c..] x, y of unit c (16 units). */
 QNNP_EXPORT void qnnp_cuda_debug_panel_tables(int n_tile, int mt, int folded, int out[50]) {
   q8::IgemmParams p{};
-  p.n_tile = n_tile, p.mt = mt, p.folded = folded;
-  fill_panel_tables(p, false);
+  p.n_tile = n_tile, p.mt = mt, p.folded = folded & 1;
+  fill_panel_tables(p, (folded & 2) != 0);  // bit 1 of `folded`: the dense single-image mode
   out[0] = p.e2_panels, out[1] = p.e2_box_rows;
   for (int k = 0; k < 4; k++) out[2 + 4 * k] = p.e2_col0[k], out[3 + 4 * k] = p.e2_width[k], out[4 + 4 * k] = p.e2_off[k], out[5 + 4 * k] = p.e2_map[k];
   for (int c = 0; c < 16; c++) out[18 + 2 * c] = (int) p.e2_unit[c].x, out[19 + 2 * c] = (int) p.e2_unit[c].y;

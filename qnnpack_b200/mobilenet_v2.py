@@ -28,6 +28,8 @@ class Layer:
     cout: int
     k: int
     stride: int
+    srcs: tuple = ()   # producers of the inputs (node indices, -1 = network input); () = the previous node
+    rowwise: bool = True  # "fc" only: rows of the flat previous output (conv stack) instead of one row per image (network)
 
     @property
     def groups(self):
@@ -47,6 +49,10 @@ class Layer:
 
     @property
     def out_h(self):
+        if self.kind == "add":
+            return self.h
+        if self.kind == "gap":
+            return 1
         return (self.h + 2 * self.pad - self.k) // self.stride + 1
 
     @property
@@ -55,6 +61,8 @@ class Layer:
 
     def ops(self, batch):
         """2*M*N*K_eff, the reference's own counter (bench/convolution.cc:99-104, bench/q8gemm.cc:108)."""
+        if self.kind in ("add", "gap"):
+            return batch * self.h * self.h * self.cin  # one add per element
         m = batch * self.out_h * self.out_h if self.kind != "fc" else batch
         return 2 * m * self.cout * self.k_eff
 
@@ -62,6 +70,10 @@ class Layer:
         """input read once + weights/bias + output written once; int32 never counts."""
         if self.kind == "fc":
             return batch * self.cin + self.cout * (self.cin + 4) + batch * self.cout
+        if self.kind == "add":
+            return 3 * batch * self.h * self.h * self.cin
+        if self.kind == "gap":
+            return batch * self.h * self.h * self.cin + batch * self.cin
         return (batch * self.h * self.h * self.cin + self.cout * (self.k_eff + 4)
                 + batch * self.out_h * self.out_h * self.cout)
 
@@ -95,6 +107,59 @@ def layers() -> list[Layer]:
     return seq
 
 
+def network() -> list[Layer]:
+    """The real MobileNetV2 graph: the 52 convolutions plus the 10 residual adds (stride-1 blocks with equal input and
+    output channels), the 7x7 global average pool and the per-image classifier — 64 operators of qnnpack.h."""
+    seq = [Layer("stem", "conv", 224, 3, 32, 3, 2, srcs=(-1,))]
+    h, c = 112, 32
+    idx = 1
+    for t, cout, n, s in ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+                          (6, 320, 1, 1)):
+        for i in range(n):
+            stride = s if i == 0 else 1
+            hidden = c * t
+            block_in = len(seq) - 1
+            if t != 1:
+                seq.append(Layer(f"b{idx}_expand", "pw", h, c, hidden, 1, 1))
+            seq.append(Layer(f"b{idx}_dw", "dw", h, hidden, hidden, 3, stride))
+            h = (h + 2 - 3) // stride + 1
+            seq.append(Layer(f"b{idx}_project", "pw", h, hidden, cout, 1, 1))
+            if stride == 1 and c == cout:
+                seq.append(Layer(f"b{idx}_add", "add", h, cout, cout, 1, 1, srcs=(block_in, len(seq) - 1)))
+            c = cout
+            idx += 1
+    seq.append(Layer("last_1x1", "pw", h, c, 1280, 1, 1))
+    seq.append(Layer("avgpool", "gap", h, 1280, 1280, 1, 1))
+    seq.append(Layer("classifier", "fc", 1, 1280, 1000, 1, 1, rowwise=False))
+    return seq
+
+
+def node_srcs(nodes, i):
+    return nodes[i].srcs or (i - 1,)
+
+
+def plan_buffers(nodes):
+    """Liveness-based assignment of node outputs to a small pool of activation buffers: a buffer is reused once every
+    consumer of the tensor it holds has run.  -> (buffer index per node, number of buffers)."""
+    last_use = {}
+    for i in range(len(nodes)):
+        for s_ in node_srcs(nodes, i):
+            last_use[s_] = i
+    free, assign, nbuf = [], [], 0
+    holder = {}
+    for i in range(len(nodes)):
+        if free:
+            b = free.pop(0)
+        else:
+            b, nbuf = nbuf, nbuf + 1
+        assign.append(b)
+        holder[i] = b
+        for s_ in set(node_srcs(nodes, i)):  # inputs whose last consumer this was become free for the NEXT node
+            if s_ >= 0 and last_use.get(s_) == i:
+                free.append(holder[s_])
+    return assign, nbuf
+
+
 def gemm_sweep() -> list[Layer]:
     """BASELINE.json configs[1]: the distinct 1x1-bottleneck GEMM shapes (+ classifier), each once."""
     seen, out = set(), []
@@ -125,6 +190,8 @@ def layer_kwargs(layer: Layer):
 def layer_params(layer: Layer, seed: int):
     """-> (kernel uint8, bias int32, create-kwargs) for qnnpack_b200.api.QnnpackLibrary."""
     rng = np.random.default_rng(seed)
+    if layer.kind in ("add", "gap"):
+        return np.zeros(0, np.uint8), np.zeros(0, np.int32), {}
     if layer.kind == "fc":
         kernel = rng.integers(0, 256, (layer.cout, layer.cin), dtype=np.uint8)
     else:
@@ -135,6 +202,16 @@ def layer_params(layer: Layer, seed: int):
 
 def create_node(lib, layer: Layer, kernel, bias):
     """One operator of the stack in any qnnpack.h implementation (product or reference)."""
+    if layer.kind == "add":  # (a - 127) + (b - 127), halved back into the uint8 range
+        st, op = lib.create("add_nc_q8", layer.cin, 127, np.float32(1.0), 127, np.float32(1.0), 127, np.float32(2.0), 0, 255)
+        if st != 0:
+            raise RuntimeError(f"create {layer.name} -> status {st}")
+        return op
+    if layer.kind == "gap":
+        st, op = lib.create("global_average_pooling_nwc_q8", layer.cin, 127, np.float32(1.0), 127, np.float32(1.0), 0, 255)
+        if st != 0:
+            raise RuntimeError(f"create {layer.name} -> status {st}")
+        return op
     kw = layer_kwargs(layer)
     if layer.kind == "fc":
         st, op = lib.create_fully_connected(kernel, bias, **kw)
@@ -147,7 +224,16 @@ def create_node(lib, layer: Layer, kernel, bias):
 
 def setup_node(lib, layer: Layer, op, batch, inputs, out):
     """inputs: [buffer] (NumPy array or device address); batch = images (rows for the classifier)."""
-    if layer.kind == "fc":
+    import ctypes as C
+
+    def ptr(b):
+        return b if isinstance(b, np.ndarray) else C.c_void_p(int(b))
+
+    if layer.kind == "add":
+        st = lib.setup("add_nc_q8", op, batch * layer.h * layer.h, ptr(inputs[0]), layer.cin, ptr(inputs[1]), layer.cin, ptr(out), layer.cin)
+    elif layer.kind == "gap":
+        st = lib.setup("global_average_pooling_nwc_q8", op, batch, layer.h * layer.h, ptr(inputs[0]), layer.cin, ptr(out), layer.cin)
+    elif layer.kind == "fc":
         st = lib.setup_fully_connected(op, batch, inputs[0], layer.cin, out, layer.cout)
     else:
         st = lib.setup_convolution(op, batch, layer.h, layer.h, inputs[0], layer.cin, out, layer.cout)
@@ -208,6 +294,50 @@ class Stack:
             if st != 0:
                 raise RuntimeError(f"setup {l.name} -> status {st}")
         return where
+
+    def run(self, asynchronous=False, hook=None):
+        for i, op in enumerate(self.ops):
+            if hook is not None:
+                hook(i, 0)
+            st = self.lib.run_async(op) if asynchronous else self.lib.run(op)
+            if st != 0:
+                raise RuntimeError(f"run {self.layers[i].name} -> status {st}")
+            if hook is not None:
+                hook(i, 1)
+
+    def delete(self):
+        for op in self.ops:
+            self.lib.delete(op)
+        self.ops = []
+
+    def total_ops(self, batch):
+        return sum(l.ops(batch) for l in self.layers)
+
+    def total_bytes(self, batch):
+        return sum(l.algorithmic_bytes(batch) for l in self.layers)
+
+
+class Network:
+    """The real MobileNetV2 graph (network()) on any qnnpack.h implementation: operators created once, activations in
+    a liveness-planned pool of buffers (plan_buffers) that the caller provides."""
+
+    def __init__(self, lib, seed: int = 0, params=None):
+        self.lib = lib
+        self.layers = network()
+        self.assign, self.nbuf = plan_buffers(self.layers)
+        self.ops = []
+        for i, l in enumerate(self.layers):
+            kernel, bias = params[i] if params is not None else layer_params(l, seed * 1000 + i)[:2]
+            self.ops.append(create_node(lib, l, kernel, bias))
+
+    def max_activation_bytes(self, batch):
+        return max(batch * l.out_elems_per_image for l in self.layers)
+
+    def setup(self, batch, buffers, first_input):
+        """buffers: self.nbuf device addresses (or NumPy arrays) of max_activation_bytes(batch) each."""
+        for i, (l, op) in enumerate(zip(self.layers, self.ops)):
+            ins = [first_input if s_ < 0 else buffers[self.assign[s_]] for s_ in node_srcs(self.layers, i)]
+            setup_node(self.lib, l, op, batch, ins, buffers[self.assign[i]])
 
     def run(self, asynchronous=False, hook=None):
         for i, op in enumerate(self.ops):

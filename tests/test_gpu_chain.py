@@ -112,3 +112,32 @@ def test_device_pointers_with_odd_bases(gpu_lib, oracle_c, case, in_off, out_off
         assert (got[:out_off] == 0xA5).all() and (got[out_off + want.size:] == 0xA5).all(), "wrote outside the output"
     finally:
         gpu_lib.delete(op)
+
+
+@pytest.mark.timeout(600, method="thread")
+@pytest.mark.parametrize("batch", [2, 5])
+def test_full_network_with_adds_and_pooling(gpu_lib, batch):
+    """The real MobileNetV2 graph (64 operators: convolutions, 10 residual adds, global average pool, per-image
+    classifier) on device buffers planned by liveness, every node's output of every image against the reference chain."""
+    import torch
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    gpu_lib.set_stream(stream.cuda_stream)
+    layers = M.network()
+    params = [M.layer_params(l, 50 + i)[:2] for i, l in enumerate(layers)]
+    net = M.Network(gpu_lib, params=params)
+    try:
+        cap = net.max_activation_bytes(batch)
+        g = torch.Generator(device=dev)
+        g.manual_seed(batch)
+        x = torch.randint(0, 256, (batch * 224 * 224 * 3,), dtype=torch.uint8, device=dev, generator=g)
+        bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(net.nbuf)]
+        net.setup(batch, [b.data_ptr() for b in bufs], x.data_ptr())
+        res = CC.check_device_network(net, params, batch, x, bufs, list(range(batch)))
+        assert res["mismatches"] == 0, res["failed_layers"]
+        assert res["layers"] == 64
+    finally:
+        net.delete()
+        gpu_lib.set_stream(0)
+        torch.cuda.set_stream(torch.cuda.default_stream())

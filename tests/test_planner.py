@@ -122,3 +122,37 @@ def test_panel_epilogue_tables(n_tile, mt, folded):
                     phys = off + r0 * width + _tma_swizzle(r * width + cc, width)  # ... as the TMA addresses it
                     assert (staging[phys:phys + 16] == (r0 + r) * 1000 + col0 + cc + np.arange(16)).all(), (col0, r0 + r, cc)
                     del logical
+
+
+@pytest.mark.parametrize("folded", [0, 1])
+@pytest.mark.parametrize("n_tile,mt", [(16, 8), (48, 5), (80, 3), (112, 2)])
+def test_dense_epilogue_tables(n_tile, mt, folded):
+    """Dense mode of the panel epilogue (narrow outputs with contiguous rows): every byte of the [row][N] image is written
+    exactly once, where the 1-D bulk store expects it, and the store phases stay conflict-free (N / 16 odd)."""
+    import numpy as np
+    from qnnpack_b200 import build
+    lib = C.CDLL(build.build())
+    out = (C.c_int * 50)()
+    lib.qnnp_cuda_debug_panel_tables(n_tile, mt, folded | 2, out)
+    assert out[0] == 0  # no panels
+    W = 32 if folded else 16
+    per_sub = (n_tile + W - 1) // W
+    img = np.full(mt * 128 * n_tile, -1, np.int64)
+    slots = {}
+    for j in range(mt):
+        for c in range(per_sub):
+            x, y = out[18 + 2 * c], out[19 + 2 * c]
+            pitch, lsh, mask = y & 0xFF, (y >> 8) & 0xFF, y >> 16
+            assert pitch == n_tile and mask == 0
+            width = min(W, n_tile - c * W)
+            for row in range(128):
+                jrow = j * 128 + row
+                a0 = (x + jrow * pitch) ^ ((row << lsh) & mask)
+                for h in range(width // 16):
+                    a = a0 + 16 * h   # (kernel: a1 = a0 + 16 in dense mode)
+                    assert (img[a:a + 16] == -1).all()
+                    img[a:a + 16] = jrow * 1000 + c * W + 16 * h + np.arange(16)
+                    slots.setdefault((j, c, h, row // 8), set()).add((a >> 4) & 7)
+    want = (np.arange(mt * 128)[:, None] * 1000 + np.arange(n_tile)[None, :]).reshape(-1)
+    assert (img == want).all()
+    assert all(len(v) == 8 for v in slots.values())
