@@ -5,11 +5,10 @@
  * load this file's shared object; the product (qnnpack_b200/csrc) never links or calls it.
  *
  * Parity pin: this restatement is checked byte-for-byte against the UNMODIFIED reference compiled
- * into oracle/_ref/libqnnpack_ref.so (tests/test_oracle_vs_ref.py, run where /root/reference
- * exists) and against the committed fixtures in tests/golden/ that were generated from that
+ * into oracle/_ref/libqnnpack_ref.so (tests/test_oracle.py, wherever oracle/_ref has been built) and against the committed fixtures in tests/golden/ that were generated from that
  * compiled reference (tests/golden/make_golden.py).  The reference has no on-disk golden vectors
  * of its own (all its tests draw from std::random_device); its deterministic known-answer tests
- * for Q31 (test/requantization-tester.h:84-246) are restated in tests/test_requantization.py.
+ * for Q31 (test/requantization-tester.h:84-246) are restated in tests/test_oracle.py.
  *
  * Every function cites the reference lines it follows (paths relative to the reference root).
  * Arithmetic is written in plain scalar C, one output element at a time, in the form the

@@ -1,7 +1,7 @@
 // q8dwconv (3x3 depthwise) and the generic direct convolution for sm_100a — CUDA-core, HBM-streaming kernels.
 //
 // Replaces (reference, paths relative to its root):
-//   src/operator-run.c:659-681 + :238-254  dwconv case -> q8dwconv_ukernel_up8x9__sse2 (src/q8dwconv/up8x9-sse2.c:14-372)
+//   src/operator-run.c:647-710 + :238-254  dwconv case -> q8dwconv_ukernel_up8x9__sse2 (src/q8dwconv/up8x9-sse2.c:14-372)
 //   src/indirection.c:81-132 (never materialised: tap -> address is computed in registers)
 //   src/q8dwconv/mp8x25-sse2.c (5x5) and grouped q8conv (src/operator-run.c:805-844 with groups > 1) via the
 //   direct kernel at the bottom.

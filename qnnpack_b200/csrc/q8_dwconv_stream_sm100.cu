@@ -1,7 +1,7 @@
 // q8dwconv 3x3, streaming dp4a kernel for sm_100a (stride 1 or 2, dilation 1, channels % 4 == 0).
 //
 // Replaces q8dwconv_ukernel_up8x9__sse2 (reference src/q8dwconv/up8x9-sse2.c:14-372) driven by
-// src/operator-run.c:659-681; the indirection buffer (src/indirection.c:81-132) is never built.
+// src/operator-run.c:647-710; the indirection buffer (src/indirection.c:81-132) is never built.
 //
 // Same integers as the reference:  acc[c] = bias'[c] + sum_taps a_tap[c] * (w_tap[c] - kzp), padded taps read izp.
 //

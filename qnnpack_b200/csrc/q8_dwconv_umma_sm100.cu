@@ -1,8 +1,8 @@
 // q8dwconv 3x3 for sm_100a on the tensor cores: depthwise convolution as block-diagonal UMMAs over TMA-staged tiles.
 //
 // Replaces (reference, paths relative to its root):
-//   src/operator-run.c:845-905  dwconv case -> q8dwconv_ukernel_up8x9__sse2 (src/q8dwconv/up8x9-sse2.c:14-482)
-//   src/indirection.c:81-150    (no pointer table: a tap is an address offset inside the staged tile)
+//   src/operator-run.c:647-710  dwconv case -> q8dwconv_ukernel_up8x9__sse2 (src/q8dwconv/up8x9-sse2.c:14-372)
+//   src/indirection.c:81-132    (no pointer table: a tap is an address offset inside the staged tile)
 // for 3x3, dilation 1, stride 1 or 2, channels % 16 == 0; other depthwise shapes keep the CUDA-core kernels
 // (q8_dwconv_stream_sm100.cu, q8_dwconv_sm100.cu).
 //
