@@ -678,7 +678,22 @@ __device__ __forceinline__ void epi2_requant16(const IgemmParams& p, const int32
 
 // One unit: W accumulator columns of the warp's 32 rows.  a0 / a1 = smem addresses of the unit's first / second 16-byte
 // chunk in this lane's staging row.
-template <int RQ, int W, bool FOLDED>
+// How an epilogue warp reports "I have read all I need from this accumulator stage":
+//   local : every lane arrives on the CTA's own tmem_empty barrier (count = threads of the epilogue group)
+//   remote: CTA pairs (q8_gemm2sm_kernel) — the UMMA-issuing thread lives in the pair's leader CTA, so ONE lane per warp
+//           arrives on the leader's barrier through its shared::cluster address (count = warps of both CTAs)
+template <bool REMOTE>
+__device__ __forceinline__ void release_tmem_stage(uint32_t tmem_empty_bar) {
+  tc_fence_before_sync();
+  if constexpr (REMOTE) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(tmem_empty_bar);
+  } else {
+    mbar_arrive(tmem_empty_bar);
+  }
+}
+
+template <int RQ, int W, bool FOLDED, bool REMOTE = false>
 __device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, uint32_t rs_taddr, uint32_t bias_addr, uint32_t a0,
                                           uint32_t a1, bool first, bool last, uint32_t tmem_empty_bar, uint32_t out_free_bar,
                                           uint32_t out_free_parity) {
@@ -691,10 +706,7 @@ __device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, 
   int32_t rowsum = 0;
   if constexpr (!FOLDED) tmem_ld1(rs_taddr, rowsum);
   tmem_ld_wait();
-  if (last) {  // this warp has read all it needs from the accumulator stage: the UMMA warps may refill it
-    tc_fence_before_sync();
-    mbar_arrive(tmem_empty_bar);
-  }
+  if (last) release_tmem_stage<REMOTE>(tmem_empty_bar);  // all read: the UMMA warps may refill the accumulator stage
   if constexpr (!FOLDED) {
     const int32_t corr = (int32_t) ((uint32_t) (-p.kzp * rowsum) + 0x80000000u);  // "U" offset rides on the bias add
 #pragma unroll
@@ -718,7 +730,7 @@ __device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, 
 
 // All units of one item for warp (quarter q, half): the two warps of a quarter take alternate units of the item's
 // (sub-tile, column block) sequence.  Everything that does not change inside the loop is an argument.
-template <int RQ, bool FOLDED>
+template <int RQ, bool FOLDED, bool REMOTE = false>
 __device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint32_t tlane, uint32_t bias_base, uint32_t staging,
                                           uint32_t row, int half, uint32_t tmem_empty_bar, uint32_t out_free_bar,
                                           uint32_t out_free_parity) {
@@ -727,8 +739,7 @@ __device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint
   const int per_sub = full + ((p.n_tile % W) ? 1 : 0);  // (W == 32: a 16-column remainder unit when n_tile % 32 == 16)
   const int units = mt_eff * per_sub;
   if (half >= units) {  // a single-unit item: nothing for the second warp of the quarter
-    tc_fence_before_sync();
-    mbar_arrive(tmem_empty_bar);
+    release_tmem_stage<REMOTE>(tmem_empty_bar);
     return;
   }
   int c = half, j = 0;
@@ -747,10 +758,10 @@ __device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint
     const uint32_t a1 = p.e2_dense ? a0 + 16u : a0 ^ 16u;
     const uint32_t taddr = tsub + (uint32_t) (c * W);
     if (c < full) {
-      epi2_unit<RQ, W, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
+      epi2_unit<RQ, W, FOLDED, REMOTE>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
                                out_free_bar, out_free_parity);
     } else {
-      epi2_unit<RQ, 16, FOLDED>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
+      epi2_unit<RQ, 16, FOLDED, REMOTE>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
                                 out_free_bar, out_free_parity);
     }
     c += 2;
@@ -1150,9 +1161,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// host launcher
-// ------------------------------------------------------------------------------------------------
 // Raises the kernel's dynamic shared-memory limit to everything the device allows beside its static shared memory.
 static cudaError_t set_max_dynamic_smem(const void* kern, int max_smem_optin) {
   cudaFuncAttributes fa;
@@ -1161,6 +1169,217 @@ static cudaError_t set_max_dynamic_smem(const void* kern, int max_smem_optin) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - (int) fa.sharedSizeBytes);
 }
 
+// ------------------------------------------------------------------------------------------------
+// large q8gemm on CTA pairs (cta_group::2)
+// ------------------------------------------------------------------------------------------------
+// For GEMMs whose weights do not fit shared memory (the tensor-bound regime: BASELINE.json's "int8 TOPS & %-of-peak on
+// q8gemm") the 128 x 256 tiles of the kernel above pull (128 + 256) K bytes from L2 per 128 x 256 x K MACs — at the
+// ~32 B/clk/SM the L2 delivered in that run this caps the tensor pipe near a third of its peak (measured 1.47 POPS of
+// 4.55).  Here two CTAs of a cluster share every UMMA: M = 256 (128 rows per CTA), N = 256 with each CTA holding HALF of
+// the B tile, so a CTA moves (128 + 128) K bytes for the same MACs — 1.5x less — and issues half the instructions.
+//   * operands: TMA 2-D boxes of 128 rows x 128 bytes of K with the 128-byte swizzle (the K-major layout UMMA reads
+//     without bank conflicts); A straight from the caller's activation matrix, B from a packed copy of the weights
+//     [n-tile][256 rows][K]: 240 output channels, one all-ones row (row sums of A: the reference's own XZP algebra,
+//     src/q8gemm/4x8c2-xzp-neon.c:26-67, pack.h:216-232) and 15 zero rows per tile;
+//   * both CTAs' loads report to the LEADER's `full` barrier (it alone issues the UMMAs); tcgen05.commit multicasts
+//     `empty` / `tmem_full` to both CTAs; epilogue warps of both CTAs release an accumulator stage on the leader's barrier;
+//   * epilogue = the panel epilogue above ("ones" form), per CTA for its own 128 rows, double-buffered in TMEM (2 x 256
+//     columns) and in the staging panels, so it overlaps the next tile's UMMAs completely.
+constexpr int k2Stages = 5;                 // 5 x (16 KB A + 16 KB B half) = 160 KB ring
+constexpr int k2StageBytes = 32768;
+constexpr int k2NTile = 240;                // output channels per tile (+ 16 rows: ones / zero) = UMMA N 256
+constexpr int k2EpiWarp0 = 2, k2EpiWarps = 8;
+constexpr int k2StoreWarp = k2EpiWarp0 + k2EpiWarps;
+constexpr int k2Threads = (k2StoreWarp + 1) * 32;  // 352
+
+struct __align__(8) Gemm2Ctl {
+  uint64_t full[k2Stages];
+  uint64_t empty[k2Stages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];   // used in the leader CTA only: 2 CTAs x 8 epilogue warps arrive
+  uint64_t out_full[2];
+  uint64_t out_free[2];
+  uint32_t tmem_base;
+};
+
+template <int RQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+    q8_gemm2sm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_a,
+                      const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ IgemmStoreMaps smaps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ Gemm2Ctl ctl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring = smem_base;                                     // k2Stages x 32 KB
+  const uint32_t staging0 = ring + k2Stages * k2StageBytes;            // 2 x staging_bytes (1024-aligned)
+  const uint32_t bias_slot = staging0 + 2 * (uint32_t) p.staging_bytes;  // 2 x 1 KB: the tile's folded biases
+
+  if (tid == 0) {
+    for (int s = 0; s < k2Stages; s++) {
+      mbar_init(smem_u32(&ctl.full[s]), 1);
+      mbar_init(smem_u32(&ctl.empty[s]), 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(smem_u32(&ctl.tmem_full[s]), 1);
+      mbar_init(smem_u32(&ctl.tmem_empty[s]), 2 * k2EpiWarps);
+      mbar_init(smem_u32(&ctl.out_full[s]), k2EpiWarps * 32);
+      mbar_init(smem_u32(&ctl.out_free[s]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(smem_u32(&ctl.tmem_base));
+  tc_fence_before_sync();
+  cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  tc_fence_after_sync();
+  const uint32_t tmem_base = ctl.tmem_base;
+
+  const int n_tiles = p.n_tiles;
+  const long long m_pairs = (p.M + 255) / 256;
+  const long long tiles = m_pairs * n_tiles;
+  const long long first = blockIdx.x >> 1, step = gridDim.x >> 1;
+  const int num_kb = (p.K + 127) / 128;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      const uint32_t lead_full0 = mapa_shared(smem_u32(&ctl.full[0]), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = first; tile < tiles; tile += step) {
+        const long long mp = tile / n_tiles;
+        const int nt = (int) (tile - mp * n_tiles);
+        const int row_a = (int) (mp * 256 + rank * 128);
+        const int row_b = nt * 256 + (int) rank * 128;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
+          const uint32_t dst = ring + (uint32_t) stage * k2StageBytes;
+          const uint32_t bar = lead_full0 + 8u * (uint32_t) stage;
+          if (rank == 0) mbar_arrive_expect_tx(smem_u32(&ctl.full[stage]), 2u * k2StageBytes);  // both CTAs' bytes
+          tma_load_2d_2sm(dst, &tmap_a, kb * 128, row_a, bar);
+          tma_load_2d_2sm(dst + 16384, &tmap_b, kb * 128, row_b, bar);
+          if (++stage == k2Stages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== UMMA issue (leader CTA) =====================================
+    if (rank == 0) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t ring_u = __shfl_sync(0xffffffffu, ring, 0);
+      const uint32_t ctl_u = __shfl_sync(0xffffffffu, smem_u32(&ctl), 0);
+      const uint32_t bar_full = ctl_u + (uint32_t) offsetof(Gemm2Ctl, full), bar_empty = ctl_u + (uint32_t) offsetof(Gemm2Ctl, empty);
+      const uint32_t bar_tfull = ctl_u + (uint32_t) offsetof(Gemm2Ctl, tmem_full);
+      const uint32_t bar_tempty = ctl_u + (uint32_t) offsetof(Gemm2Ctl, tmem_empty);
+      const uint32_t idesc = umma_idesc_i8(256, 256, false, false);  // u8 x u8 ("ones" algebra), M = 256 over the pair
+      int stage = 0, as = 0;
+      uint32_t phase = 0, as_phase = 0;
+      for (long long tile = first; tile < tiles; tile += step) {
+        mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_u + (uint32_t) as * 256u;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait_parked(bar_full + 8u * (uint32_t) stage, phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = ring_u + (uint32_t) stage * k2StageBytes;
+          if (elect_one()) {
+            const uint64_t ad = umma_desc_kmajor_sw128(a_addr), bd = umma_desc_kmajor_sw128(a_addr + 16384);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++)  // 32 bytes of K per UMMA: +2 in the 16-byte-granular start address
+              umma_i8_2sm(d_tmem, ad + (uint64_t) (2 * k4), bd + (uint64_t) (2 * k4), idesc, (kb | k4) != 0 ? 1u : 0u);
+            umma_commit_2sm(bar_empty + 8u * (uint32_t) stage, 3);
+            if (kb == num_kb - 1) umma_commit_2sm(bar_tfull + 8u * (uint32_t) as, 3);
+          }
+          __syncwarp();
+          if (++stage == k2Stages) stage = 0, phase ^= 1;
+        }
+        as ^= 1;
+        if (as == 0) as_phase ^= 1;
+      }
+    }
+  } else if (warp < k2StoreWarp) {
+    // ===================================== epilogue (8 warps per CTA) =====================================
+    const int ew = warp - k2EpiWarp0;
+    const int q = warp & 3, half = ew >> 2;   // TMEM lane quarter = warp index mod 4 (hardware rule)
+    const uint32_t row = (uint32_t) (q * 32 + lane);
+    const uint32_t lead_tempty0 = mapa_shared(smem_u32(&ctl.tmem_empty[0]), 0);
+    int as = 0;
+    uint32_t as_phase = 0, k = 0;
+    for (long long tile = first; tile < tiles; tile += step, k++) {
+      const long long mp = tile / n_tiles;
+      const int nt = (int) (tile - mp * n_tiles);
+      const uint32_t buf = k & 1;
+      // this tile's folded biases -> smem slot (the previous user of the slot, tile k - 2, is long done: its epilogue
+      // finished before tile k - 1's, and every warp passes the named barrier of tile k - 1 before reaching this one)
+      const uint32_t slot = bias_slot + buf * 1024u;
+      for (int i = ew * 32 + lane; i < k2NTile; i += k2EpiWarps * 32)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(slot + 4u * (uint32_t) i), "r"(__ldg(p.bias + (size_t) nt * k2NTile + i)) : "memory");
+      named_bar_sync(1, k2EpiWarps * 32);
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
+      tc_fence_after_sync();
+      epi2_item<RQ, false, true>(p, 1, tmem_base + (uint32_t) as * 256u + ((uint32_t) (q * 32) << 16), slot,
+                                 staging0 + buf * (uint32_t) p.staging_bytes, row, half, lead_tempty0 + 8u * (uint32_t) as,
+                                 smem_u32(&ctl.out_free[buf]), ((k >> 1) & 1) ^ 1);
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&ctl.out_full[buf]));
+      as ^= 1;
+      if (as == 0) as_phase ^= 1;
+    }
+  } else {
+    // ===================================== output stores =====================================
+    if (lane == 0) {
+      uint32_t k = 0;
+      for (long long tile = first; tile < tiles; tile += step, k++) {
+        const long long mp = tile / n_tiles;
+        const int nt = (int) (tile - mp * n_tiles);
+        const uint32_t buf = k & 1;
+        mbar_wait_relaxed(smem_u32(&ctl.out_full[buf]), (k >> 1) & 1, 20);
+        const uint32_t staging = staging0 + buf * (uint32_t) p.staging_bytes;
+        const long long m0 = mp * 256 + rank * 128;
+        for (int pk = 0; pk < p.e2_panels; pk++) {
+          const int col = nt * k2NTile + p.e2_col0[pk];
+          if (col >= p.goc || m0 >= p.M) break;
+          tma_store_2d(&smaps.m[p.e2_map[pk]][0], staging + (uint32_t) p.e2_off[pk], col, (int) m0);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(smem_u32(&ctl.out_free[buf]));
+      }
+      bulk_wait<0>();
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();   // both CTAs are done with the pair's tensor memory and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+cudaError_t launch_q8_gemm2sm(const IgemmParams& p, const void* tmap_a, const void* tmap_b, const IgemmStoreMaps& smaps, int clusters,
+                              int max_smem_optin, cudaStream_t stream) {
+  alignas(64) CUtensorMap ta, tb;
+  memcpy(&ta, tmap_a, sizeof(ta));
+  memcpy(&tb, tmap_b, sizeof(tb));
+  const int smem = k2Stages * k2StageBytes + 2 * p.staging_bytes + 2048 + 1024;
+  if (p.rq_mode == 5) {
+    auto kern = q8_gemm2sm_kernel<5>;
+    static cudaError_t attr_status = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), max_smem_optin);
+    if (attr_status != cudaSuccess) return attr_status;
+    kern<<<2 * clusters, k2Threads, smem, stream>>>(p, ta, tb, smaps);
+  } else {
+    auto kern = q8_gemm2sm_kernel<6>;
+    static cudaError_t attr_status = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), max_smem_optin);
+    if (attr_status != cudaSuccess) return attr_status;
+    kern<<<2 * clusters, k2Threads, smem, stream>>>(p, ta, tb, smaps);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------------
 // The dynamic-smem limit is a property of the kernel instantiation, not of a launch: it is raised ONCE to the device's
 // opt-in maximum (setting it per launch to the operator's size raced between host threads running different operators).
 template <int MODE, int VEC>

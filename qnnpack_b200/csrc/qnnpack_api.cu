@@ -36,6 +36,8 @@ namespace q8 {
 cudaError_t measure_int8_peak(int num_sms, int iters, int reps, cudaStream_t stream, double* tops, double* ms_out);
 cudaError_t launch_q8_igemm(const IgemmParams& p, int mode, int vec, const void* tmap_a, const IgemmStoreMaps* store_maps,
                             int grid, int max_smem_optin, cudaStream_t stream);
+cudaError_t launch_q8_gemm2sm(const IgemmParams& p, const void* tmap_a, const void* tmap_b, const IgemmStoreMaps& smaps, int clusters,
+                              int max_smem_optin, cudaStream_t stream);
 }
 
 #define QNNP_EXPORT extern "C" __attribute__((visibility("default")))
@@ -158,6 +160,20 @@ bool make_tmap_out(void* tm, uint8_t* out, size_t M, size_t N, size_t out_stride
                                                            : width == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   return fn((CUtensorMap*) tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, out, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Row-major u8 matrix [rows][stride] (first K bytes of a row used) as a 2-D tensor {K, rows}; box = 128 bytes of K x 128
+// rows, 128-byte swizzle: the K-major SWIZZLE_128B operand image of the CTA-pair GEMM.  Out-of-range bytes read zero.
+bool make_tmap_kmajor_sw128(CUtensorMap* tm, const uint8_t* base, size_t rows, size_t K, size_t stride) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t) K, (cuuint64_t) rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t) stride};
+  const cuuint32_t box[2] = {128, 128};
+  const cuuint32_t estride[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), gdim, gstride, box, estride,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
@@ -357,6 +373,10 @@ struct qnnp_operator {
   int b_resident = 0, num_stages = 0, stage_bytes = 0;
   int smem_b_off = 0, smem_bias_off = 0, smem_a_off = 0, smem_stage_off = 0, staging_bytes = 0, smem_total = 0;
   bool bulk_capable = false;
+  // CTA-pair GEMM (large weights): packed copy [n_tiles2][256 rows][K] (240 channels, ones row, zero rows) + folded biases
+  uint8_t* d_w2 = nullptr;
+  int32_t* d_bias2 = nullptr;
+  int n_tiles2 = 0;
   int c_pad = 0;  // dw
   uint32_t* d_dw_wa = nullptr;  // dw streaming kernel: packed taps, operands A and B
   uint32_t* d_dw_wb = nullptr;
@@ -400,6 +420,8 @@ void free_operator(qnnp_operator* op) {
   if (op == nullptr) return;
   cudaFree(op->d_weights);
   cudaFree(op->d_bias);
+  cudaFree(op->d_w2);
+  cudaFree(op->d_bias2);
   cudaFree(op->d_dw_wa);
   cudaFree(op->d_dw_wb);
   cudaFree(op->d_dwtc_w);
@@ -679,6 +701,26 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
   if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias, fbias.size() * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMemcpy(op->d_weights, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(op->d_bias, fbias.data(), fbias.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  // Weights that cannot stay resident in shared memory (large GEMMs): a second packing for the CTA-pair kernel
+  // (q8_gemm2sm_kernel) — plain K-contiguous rows, so the TMA loads them with the 128-byte swizzle itself.
+  if (e == cudaSuccess && !op->b_resident && op->groups == 1 && op->kh * op->kw == 1 && (op->K % 16) == 0 &&
+      getenv("QNNP_CUDA_NO_GEMM2SM") == nullptr) {
+    const size_t K = (size_t) op->K, N = op->goc;
+    const int nt2 = (int) ceil_div(N, 240);
+    std::vector<uint8_t> w2((size_t) nt2 * 256 * K, 0);
+    std::vector<int32_t> b2((size_t) nt2 * 240, 0);
+    for (size_t n = 0; n < N; n++) {
+      const size_t t = n / 240, r = n % 240;
+      memcpy(w2.data() + (t * 256 + r) * K, kernel + n * K, K);
+      b2[n] = fold_bias(bias[n], K, op->izp, op->kzp, kernel + n * K);
+    }
+    for (int t = 0; t < nt2; t++) memset(w2.data() + ((size_t) t * 256 + 240) * K, 1, K);  // row 240: ones -> row sums of A
+    e = cudaMalloc((void**) &op->d_w2, w2.size());
+    if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias2, b2.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(op->d_w2, w2.data(), w2.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(op->d_bias2, b2.data(), b2.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    op->n_tiles2 = nt2;
+  }
   return map_cuda(e, "uploading packed weights");
 }
 
@@ -804,7 +846,7 @@ enum qnnp_status pack_direct(qnnp_operator* op, const uint8_t* kernel, const int
 // included, on every run: SURVEY.md §3.4 puts this work in setup, like the reference's indirection-buffer setup,
 // src/convolution.c:428-492.)
 enum PlanPath {
-  kPlanNone = 0, kPlanIgemm, kPlanDwUmma, kPlanDwStream, kPlanDwGeneric, kPlanDirect,
+  kPlanNone = 0, kPlanIgemm, kPlanGemm2sm, kPlanDwUmma, kPlanDwStream, kPlanDwGeneric, kPlanDirect,
   kPlanAdd, kPlanGavgPool, kPlanPool2d, kPlanMap, kPlanSoftargmax, kPlanShuffle
 };
 
@@ -861,6 +903,7 @@ struct qnnp_launch_plan {
   int ig_mode = 0, ig_vec = 0;
   bool has_tmap_a = false, has_smaps = false;
   alignas(64) CUtensorMap tmap_a;
+  alignas(64) CUtensorMap tmap_b;
   q8::IgemmStoreMaps smaps;
   // depthwise
   q8::DwTcParams tp{};
@@ -1020,6 +1063,38 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       pl.ig = p;
       pl.ig_mode = mode, pl.ig_vec = vec;
       pl.path = kPlanIgemm;
+      // large GEMMs (weights not resident): the CTA-pair kernel, when the operands can be described to the TMA
+      if (op->d_w2 != nullptr && mode == q8::kModeGemm && (op->rq_mode == 5 || op->rq_mode == 6) && M >= 256 &&
+          ((uintptr_t) in % 16) == 0 && (op->in_stride % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->out_stride % 16) == 0 &&
+          g_lib.dbg_acc == nullptr && !env_set("QNNP_CUDA_NO_GEMM2SM")) {
+        q8::IgemmParams q = p;
+        q.n_tile = 240, q.n_mma = 256, q.n_tiles = op->n_tiles2, q.mt = 1, q.folded = 0, q.has_corr = 1;
+        q.bias = op->d_bias2;
+        q.staging_bytes = q8::kTileM * 240;
+        q.out_mode = 2;
+        fill_panel_tables(q, false);
+        bool ok = make_tmap_kmajor_sw128(&pl.tmap_a, in, M, (size_t) op->K, op->in_stride) &&
+            make_tmap_kmajor_sw128(&pl.tmap_b, op->d_w2, (size_t) op->n_tiles2 * 256, (size_t) op->K, (size_t) op->K);
+        bool done[4] = {false, false, false, false};
+        for (int k = 0; k < q.e2_panels && ok; k++) {
+          const int cls = q.e2_map[k];
+          if (done[cls]) continue;
+          done[cls] = true;
+          ok = make_tmap_out(&pl.smaps.m[cls][0], out, M, op->goc, op->out_stride, q.e2_width[k], q.e2_box_rows);
+        }
+        if (ok) {
+          const long long tiles = (long long) ceil_div(M, 256) * op->n_tiles2;
+          long long clusters = g_lib.num_sms / 2;
+          if (clusters > tiles) clusters = tiles;
+          if (const char* ev = getenv("QNNP_CUDA_MAX_CTAS")) {
+            const long long v = atoll(ev) / 2;
+            if (v >= 1 && v < clusters) clusters = v;
+          }
+          pl.ig = q;
+          pl.grid = (int) clusters;
+          pl.path = kPlanGemm2sm;
+        }
+      }
       break;
     }
     case kKindDw3x3: {
@@ -1223,6 +1298,9 @@ enum qnnp_status launch(qnnp_operator* op, const uint8_t* in, const uint8_t* in2
     case kPlanIgemm:
       e = q8::launch_q8_igemm(pl.ig, pl.ig_mode, pl.ig_vec, pl.has_tmap_a ? &pl.tmap_a : nullptr,
                               pl.has_smaps ? &pl.smaps : nullptr, pl.grid, g_lib.max_smem_optin, stream);
+      break;
+    case kPlanGemm2sm:
+      e = q8::launch_q8_gemm2sm(pl.ig, &pl.tmap_a, &pl.tmap_b, pl.smaps, pl.grid, g_lib.max_smem_optin, stream);
       break;
     case kPlanDwUmma:
       e = q8::launch_q8_dwconv3x3_umma(pl.tp, &pl.dw_tmap, pl.grid, g_lib.max_smem_optin, stream);
