@@ -36,6 +36,21 @@ __device__ __forceinline__ uint32_t add_quantize(uint32_t a, uint32_t b, const A
   return (uint32_t) y;
 }
 
+// The same value with the rounding written as one add and one shift, valid while acc + 2^(shift-1) cannot overflow
+// (shift <= 22: |acc| <= 255 * (2^22 - 1) * 2 < 2^31 - 2^21):  (acc >> s) + [rem > threshold] == (acc + 2^(s-1) - [acc < 0]) >> s.
+// Returns acc' + zero point, unclamped (the caller saturates four of them into a word, then clamps the word).
+__device__ __forceinline__ int32_t add_quantize_fast(uint32_t a, uint32_t b, const AddParams& p) {
+  const int32_t acc = (int32_t) ((uint32_t) p.zero_point_product + a * p.a_multiplier + b * p.b_multiplier);
+  return ((acc + p.remainder_threshold + 1 + (acc >> 31)) >> p.shift) + p.y_zero_point;
+}
+
+__device__ __forceinline__ uint32_t pack_sat4(int32_t a, int32_t b, int32_t c, int32_t d) {
+  uint32_t hi, out;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(d), "r"(c));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+  return out;
+}
+
 // requantization.h:482-498
 __device__ __forceinline__ uint32_t avgpool_quantize(int32_t n, const AvgQuant& q) {
   const int64_t product = (int64_t) n * (int64_t) q.multiplier;
@@ -75,7 +90,7 @@ __device__ __forceinline__ void split_item(long long i, int pieces_per_row, int 
 }
 
 // ---- add ------------------------------------------------------------------------------------------------------------
-template <int VEC>
+template <int VEC, bool FAST>
 __global__ void __launch_bounds__(kThreads) q8_add_kernel(const __grid_constant__ AddParams p) {
   const long long i = (long long) blockIdx.x * kThreads + threadIdx.x;
   if (i >= p.rows * p.pieces_per_row) return;
@@ -90,6 +105,13 @@ __global__ void __launch_bounds__(kThreads) q8_add_kernel(const __grid_constant_
   for (int w = 0; w < NW; w++) {
     if constexpr (VEC == 1) {
       y[w] = add_quantize(a[w], b[w], p);
+    } else if constexpr (FAST) {
+      int32_t r[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) r[k] = add_quantize_fast(__byte_perm(a[w], 0, 0x4440 + k), __byte_perm(b[w], 0, 0x4440 + k), p);
+      // saturate to [0, 255] while packing, then clamp the four bytes at once: identical to clamping each int32 to
+      // [y_min, y_max] because 0 <= y_min < y_max <= 255
+      y[w] = __vminu4(__vmaxu4(pack_sat4(r[0], r[1], r[2], r[3]), (uint32_t) p.y_min * 0x01010101u), (uint32_t) p.y_max * 0x01010101u);
     } else {
       y[w] = 0;
 #pragma unroll
@@ -182,11 +204,24 @@ __global__ void __launch_bounds__(kThreads) q8_gavgpool_kernel(const __grid_cons
   int32_t acc[CV];
 #pragma unroll
   for (int k = 0; k < CV; k++) acc[k] = p.bias;
-  for (long long w = 0; w < p.width; w++) {
+  long long w = 0;
+  if constexpr (CV == 4) {
+    // seven pixels per step, loads first: seven independent requests in flight per thread (a 7x7 map is seven steps)
+    for (; w + 7 <= p.width; w += 7) {
+      uint32_t v[7];
+#pragma unroll
+      for (int i = 0; i < 7; i++) v[i] = *reinterpret_cast<const uint32_t*>(x + (w + i) * p.x_stride);
+#pragma unroll
+      for (int i = 0; i < 7; i++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[k] = __dp4a(v[i], (uint32_t) (1u << (8 * k)), (uint32_t) acc[k]);  // + byte k
+    }
+  }
+  for (; w < p.width; w++) {
     if constexpr (CV == 4) {
       const uint32_t v = *reinterpret_cast<const uint32_t*>(x + w * p.x_stride);
 #pragma unroll
-      for (int k = 0; k < 4; k++) acc[k] = __dp4a(v, (uint32_t) (1u << (8 * k)), (uint32_t) acc[k]);  // + byte k (u8 x u8 dot product with a unit vector)
+      for (int k = 0; k < 4; k++) acc[k] = __dp4a(v, (uint32_t) (1u << (8 * k)), (uint32_t) acc[k]);
     } else {
       acc[0] += x[w * p.x_stride];
     }
@@ -270,12 +305,15 @@ __global__ void __launch_bounds__(kThreads) q8_pool2d_kernel(const __grid_consta
 cudaError_t launch_q8_add(const AddParams& p, int vec, cudaStream_t stream) {
   const long long work = p.rows * p.pieces_per_row;
   if (work == 0) return cudaSuccess;
+  const bool fast = p.shift <= 22;
   if (vec == 16) {
-    q8_add_kernel<16><<<blocks_for(work), kThreads, 0, stream>>>(p);
+    if (fast) q8_add_kernel<16, true><<<blocks_for(work), kThreads, 0, stream>>>(p);
+    else q8_add_kernel<16, false><<<blocks_for(work), kThreads, 0, stream>>>(p);
   } else if (vec == 4) {
-    q8_add_kernel<4><<<blocks_for(work), kThreads, 0, stream>>>(p);
+    if (fast) q8_add_kernel<4, true><<<blocks_for(work), kThreads, 0, stream>>>(p);
+    else q8_add_kernel<4, false><<<blocks_for(work), kThreads, 0, stream>>>(p);
   } else {
-    q8_add_kernel<1><<<blocks_for(work), kThreads, 0, stream>>>(p);
+    q8_add_kernel<1, false><<<blocks_for(work), kThreads, 0, stream>>>(p);
   }
   return cudaGetLastError();
 }

@@ -733,10 +733,10 @@ __device__ __forceinline__ void epi2_unit(const IgemmParams& p, uint32_t taddr, 
 template <int RQ, bool FOLDED, bool REMOTE = false>
 __device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint32_t tlane, uint32_t bias_base, uint32_t staging,
                                           uint32_t row, int half, uint32_t tmem_empty_bar, uint32_t out_free_bar,
-                                          uint32_t out_free_parity) {
+                                          uint32_t out_free_parity, int n_tile) {
   constexpr int W = FOLDED ? 32 : 16;
-  const int full = p.n_tile / W;
-  const int per_sub = full + ((p.n_tile % W) ? 1 : 0);  // (W == 32: a 16-column remainder unit when n_tile % 32 == 16)
+  const int full = n_tile / W;
+  const int per_sub = full + ((n_tile % W) ? 1 : 0);  // (W == 32: a 16-column remainder unit when n_tile % 32 == 16)
   const int units = mt_eff * per_sub;
   if (half >= units) {  // a single-unit item: nothing for the second warp of the quarter
     release_tmem_stage<REMOTE>(tmem_empty_bar);
@@ -758,10 +758,10 @@ __device__ __forceinline__ void epi2_item(const IgemmParams& p, int mt_eff, uint
     const uint32_t a1 = p.e2_dense ? a0 + 16u : a0 ^ 16u;
     const uint32_t taddr = tsub + (uint32_t) (c * W);
     if (c < full) {
-      epi2_unit<RQ, W, FOLDED, REMOTE>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
+      epi2_unit<RQ, W, FOLDED, REMOTE>(p, taddr, tsub + n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
                                out_free_bar, out_free_parity);
     } else {
-      epi2_unit<RQ, 16, FOLDED, REMOTE>(p, taddr, tsub + p.n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
+      epi2_unit<RQ, 16, FOLDED, REMOTE>(p, taddr, tsub + n_tile, bias_base + (uint32_t) (c * W) * 4, a0, a1, first, last, tmem_empty_bar,
                                 out_free_bar, out_free_parity);
     }
     c += 2;
@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           tc_fence_after_sync();
           epi2_item<RQ, FOLDED>(p, it.mt_eff, tmem_base + as * p.acc_stride + ((uint32_t) (q * 32) << 16),
                                 bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4, staging, row, half,
-                                smem_u32(&ctl.tmem_empty[as]), smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1);
+                                smem_u32(&ctl.tmem_empty[as]), smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1, p.n_tile);
           fence_proxy_async_smem();  // staging writes (generic proxy) -> tensor stores (async proxy)
           mbar_arrive(smem_u32(&ctl.out_full[pair]));
         }
@@ -1250,7 +1250,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
         const long long mp = tile / n_tiles;
         const int nt = (int) (tile - mp * n_tiles);
         const int row_a = (int) (mp * 256 + rank * 128);
-        const int row_b = nt * 256 + (int) rank * 128;
+        // the pair's B operand has n_mma rows, CTA r supplying rows [r * n_mma / 2, (r + 1) * n_mma / 2): the last (ragged)
+        // n-tile runs a narrower UMMA (its real columns rounded to 16, plus the 16 rows holding the ones row)
+        const int n_mma = nt == n_tiles - 1 ? p.e2_last_nmma : 256;
+        const int row_b = nt * 256 + (int) rank * (n_mma >> 1);
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
           const uint32_t dst = ring + (uint32_t) stage * k2StageBytes;
@@ -1271,10 +1274,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
       const uint32_t bar_full = ctl_u + (uint32_t) offsetof(Gemm2Ctl, full), bar_empty = ctl_u + (uint32_t) offsetof(Gemm2Ctl, empty);
       const uint32_t bar_tfull = ctl_u + (uint32_t) offsetof(Gemm2Ctl, tmem_full);
       const uint32_t bar_tempty = ctl_u + (uint32_t) offsetof(Gemm2Ctl, tmem_empty);
-      const uint32_t idesc = umma_idesc_i8(256, 256, false, false);  // u8 x u8 ("ones" algebra), M = 256 over the pair
+      const uint32_t idesc_full = umma_idesc_i8(256, 256, false, false);  // u8 x u8 ("ones" algebra), M = 256 over the pair
+      const uint32_t idesc_last = umma_idesc_i8(256, (uint32_t) p.e2_last_nmma, false, false);
       int stage = 0, as = 0;
       uint32_t phase = 0, as_phase = 0;
       for (long long tile = first; tile < tiles; tile += step) {
+        const uint32_t idesc = (int) (tile % n_tiles) == n_tiles - 1 ? idesc_last : idesc_full;
         mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_u + (uint32_t) as * 256u;
@@ -1319,7 +1324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
       tc_fence_after_sync();
       epi2_item<RQ, false, true>(p, 1, tmem_base + (uint32_t) as * 256u + ((uint32_t) (q * 32) << 16), slot,
                                  staging0 + buf * (uint32_t) p.staging_bytes, row, half, lead_tempty0 + 8u * (uint32_t) as,
-                                 smem_u32(&ctl.out_free[buf]), ((k >> 1) & 1) ^ 1);
+                                 smem_u32(&ctl.out_free[buf]), ((k >> 1) & 1) ^ 1, nt == n_tiles - 1 ? p.e2_last_nmma - 16 : k2NTile);
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&ctl.out_full[buf]));
       as ^= 1;

@@ -81,6 +81,7 @@ struct IgemmParams {
   //   x = byte offset of the unit's first 16-byte chunk relative to the staging buffer, for row 0 of sub-tile 0
   //   y = pitch | lsh << 8 | mask << 16   (swizzle: chunk bits ^= (row << lsh) & mask)
   uint2 e2_unit[16];
+  int e2_last_nmma;           // CTA-pair GEMM: UMMA N of the last n-tile (real columns rounded up to 16, + 16 for the ones row)
 
   int izp, kzp;
   Q8Requant rq;

@@ -714,7 +714,11 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
       memcpy(w2.data() + (t * 256 + r) * K, kernel + n * K, K);
       b2[n] = fold_bias(bias[n], K, op->izp, op->kzp, kernel + n * K);
     }
-    for (int t = 0; t < nt2; t++) memset(w2.data() + ((size_t) t * 256 + 240) * K, 1, K);  // row 240: ones -> row sums of A
+    // ones row (row sums of A) right after the tile's real channels rounded to 16: row 240, or earlier in the ragged last tile
+    for (int t = 0; t < nt2; t++) {
+      const size_t real = t == nt2 - 1 ? N - (size_t) t * 240 : 240;
+      memset(w2.data() + ((size_t) t * 256 + round_up(real, 16)) * K, 1, K);
+    }
     e = cudaMalloc((void**) &op->d_w2, w2.size());
     if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_bias2, b2.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(op->d_w2, w2.data(), w2.size(), cudaMemcpyHostToDevice);
@@ -1064,7 +1068,9 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       pl.ig_mode = mode, pl.ig_vec = vec;
       pl.path = kPlanIgemm;
       // large GEMMs (weights not resident): the CTA-pair kernel, when the operands can be described to the TMA
-      if (op->d_w2 != nullptr && mode == q8::kModeGemm && (op->rq_mode == 5 || op->rq_mode == 6) && M >= 256 &&
+      // (8 epilogue warps per CTA: the pair kernel wins where the tensor pipe is the long pole, i.e. deep K)
+      const int g2_min_k = getenv("QNNP_CUDA_GEMM2SM_MIN_K") != nullptr ? atoi(getenv("QNNP_CUDA_GEMM2SM_MIN_K")) : 1024;
+      if (op->d_w2 != nullptr && op->K >= g2_min_k && mode == q8::kModeGemm && (op->rq_mode == 5 || op->rq_mode == 6) && M >= 256 &&
           ((uintptr_t) in % 16) == 0 && (op->in_stride % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->out_stride % 16) == 0 &&
           g_lib.dbg_acc == nullptr && !env_set("QNNP_CUDA_NO_GEMM2SM")) {
         q8::IgemmParams q = p;
@@ -1072,6 +1078,7 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
         q.bias = op->d_bias2;
         q.staging_bytes = q8::kTileM * 240;
         q.out_mode = 2;
+        q.e2_last_nmma = (int) round_up(op->goc - (size_t) (op->n_tiles2 - 1) * 240, 16) + 16;
         fill_panel_tables(q, false);
         bool ok = make_tmap_kmajor_sw128(&pl.tmap_a, in, M, (size_t) op->K, op->in_stride) &&
             make_tmap_kmajor_sw128(&pl.tmap_b, op->d_w2, (size_t) op->n_tiles2 * 256, (size_t) op->K, (size_t) op->K);
