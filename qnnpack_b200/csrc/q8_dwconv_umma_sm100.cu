@@ -339,24 +339,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     int as = 0;
     uint32_t as_phase = 0;
     ItemPos pos = first_pos(p, first);
-    // The item position changes fastest in the channel block, then in the x tile, then in (y tile, image): with the
-    // contiguous schedule the values below are recomputed only when THEIR digit changes, not once per item
-    //   per (image block, y tile): the lane's row validity and row class, the origin of the tile row in the output
-    //   per x tile               : the origin of the tile
-    uint8_t* row_base = nullptr;    // warp-uniform: output address of (image n0, row oy0, column 0, channel 0)
-    uint8_t* tile_base = nullptr;   // ... of column ox0
+    // values that depend on the SPATIAL tile only: with the contiguous schedule (channel block fastest) they change once
+    // every `cblocks` items, so they are recomputed only then
+    uint8_t* tile_base = nullptr;   // warp-uniform origin of the spatial tile in the output tensor (channel 0)
     bool row_ok = false;
     uint32_t rm_row = 0;            // row class * 8 * channels: index of this lane's row of bias_cls, column class 0
-    int cur_yt = -1, cur_nb = -1, cur_xt = -1;
-    int j_cur = -1;                 // sub-tile whose column values (below) are current
-    uint32_t cm_term = 0, dst_off = 0;
-    bool valid = false;
     for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
       const DwItem it = make_item(p, pos);
       const int c0 = it.cb * p.G * 16;
-      if (pos.yt != cur_yt || pos.nb != cur_nb) {
-        cur_yt = pos.yt, cur_nb = pos.nb, cur_xt = -1;
-        row_base = p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w) * p.out_stride;
+      if (item == first || it.cb == 0) {
+        tile_base = p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w + it.ox0) * p.out_stride;
         const int oy = it.oy0 + oyl;
         row_ok = img < p.nb && it.n0 + img < p.batch && oy < p.out_h;
         // row class: bit k set iff input row iy0 + k lies inside the image (taps below 0 / at or above in_h are padding)
@@ -364,11 +356,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int rlo = iy0 < 0 ? -iy0 : 0, rhi = iy0 + 3 - p.in_h > 0 ? iy0 + 3 - p.in_h : 0;
         const uint32_t rm = rhi >= 3 ? 0u : (((7u << rlo) & 7u) & (7u >> rhi));
         rm_row = rm * 8u * (uint32_t) p.channels;
-      }
-      if (pos.xt != cur_xt) {
-        cur_xt = pos.xt;
-        tile_base = row_base + (size_t) it.ox0 * p.out_stride;
-        j_cur = -1;
       }
       uint8_t* const obase = tile_base + c0;
       const uint32_t bias_row = rm_row + (uint32_t) c0;
@@ -384,20 +371,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_before_sync();
         mbar_arrive(empty_bar);
       }
+      int j_cur = -1;
+      uint32_t bias_idx = 0, dst_off = 0;
+      bool valid = false;
       for (int un = h; un < units; un += 4) {
         int j, gi;
         unit_split(un, it.mt_eff, inv, j, gi);
-        if (j != j_cur) {  // (j_cur survives from item to item: the channel blocks of a tile reuse the column values)
+        if (j != j_cur) {
           j_cur = j;
           const int ox = it.ox0 + 8 * j + px;
           const int ix0 = ox * S - p.pad_left;
           const int clo = ix0 < 0 ? -ix0 : 0, chi = ix0 + 3 - p.in_w > 0 ? ix0 + 3 - p.in_w : 0;
           const uint32_t cm = chi >= 3 ? 0u : (((7u << clo) & 7u) & (7u >> chi));
-          cm_term = cm * (uint32_t) p.channels;
+          bias_idx = bias_row + cm * (uint32_t) p.channels;
           dst_off = lane_off + (uint32_t) j * sub_step;
           valid = row_ok && ox < p.out_w;
         }
-        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, p.bias_cls + (bias_row + cm_term + (uint32_t) gi * 16u),
+        epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, p.bias_cls + (bias_idx + (uint32_t) gi * 16u),
                               obase + (dst_off + (uint32_t) gi * 16u), valid, un + 4 >= units, empty_bar);
       }
       as ^= 1;
