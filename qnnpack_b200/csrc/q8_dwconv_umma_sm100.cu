@@ -56,6 +56,35 @@ struct __align__(8) Ctl {
   uint32_t tmem_base;
 };
 
+// What every role needs to know about a work item, computed ONCE by the TMA producer thread (which decodes the item
+// anyway) and handed to the 7 UMMA-issuing and 16 epilogue warps through a small shared-memory ring.  Round 2: before,
+// each of those 23 warps re-derived it per item (mixed-radix stepping, tail clamps, a 64-bit output origin: ~80-140
+// instructions per warp and item — a quarter of everything the kernel executed, profiles/r2c_dw_umma_first2).
+// Slot of the k-th item of a CTA: k mod kDescSlots.  A slot is rewritten num_stages + 2 items later at the earliest: the
+// producer runs at most num_stages items ahead of the UMMAs, which run at most 2 (accumulator stages) ahead of the
+// epilogue's last tensor-memory read of an item — and every reader has copied the slot to registers before that.
+// Visibility: the producer writes the slot before its arrive.expect_tx on the stage's `full` barrier (release); the UMMA
+// warps read it after their wait on `full` (acquire), the epilogue warps after their wait on `tmem_full`, which the UMMA
+// warps signal after that.
+struct __align__(16) ItemDesc {
+  uint64_t tile_base;  // output address of (image n0, row oy0, column ox0, channel 0)
+  int32_t n0, oy0;
+  int32_t ox0, c0;
+  int32_t mt_eff, g_eff;
+  uint32_t inv;        // ceil(2^16 / mt_eff): unit index -> (sub-tile, channel group)
+  int32_t units;
+  int32_t pad[2];
+};
+constexpr int kDescSlots = kDwTcMaxStages + 2;
+
+__device__ __forceinline__ ItemDesc load_desc(const ItemDesc* d) {
+  ItemDesc r;
+  const uint4* s4 = reinterpret_cast<const uint4*>(d);
+  uint4* r4 = reinterpret_cast<uint4*>(&r);
+  r4[0] = s4[0], r4[1] = s4[1], r4[2] = s4[2];
+  return r;
+}
+
 struct DwItem {
   int cb;       // channel block (G groups of 16 channels)
   int n0;       // first image
@@ -195,8 +224,8 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
 // moved it across with an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, ~30 instructions per UMMA — 17 % of all the
 // instructions this kernel executed, profiles/r1h_dwconv_umma_first2.)
 template <int NB>
-__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t smem_base_v, uint32_t tmem_base_v, int w_v,
-                                         uint32_t first, uint32_t step, uint32_t total) {
+__device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const ItemDesc* descs, uint32_t smem_base_v,
+                                         uint32_t tmem_base_v, int w_v, uint32_t first, uint32_t step, uint32_t total) {
   const int w = __shfl_sync(0xffffffffu, w_v, 0);
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base_v, 0);
   const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_base_v, 0);
@@ -210,27 +239,28 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, uint32_t
     adesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], (uint32_t) p.sbo);
     bdesc[u] = umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 128);
   }
-  int stage = 0, as = 0;
+  int stage = 0, as = 0, dslot = 0;
   uint32_t phase = 0, as_phase = 0;
-  ItemPos pos = first_pos(p, first);
-  for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
-    const DwItem it = make_item(p, pos);
-    const int units = it.mt_eff * it.g_eff;
-    const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
+  for (uint32_t item = first; item < total; item += step) {
+    mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
+    mbar_wait_parked(bar_full + 8u * (uint32_t) stage, phase);
+    tc_fence_after_sync();
+    // mt_eff / units / inv of the item, from the producer's descriptor (same address in every lane: one broadcast load)
+    const int mt_eff = __shfl_sync(0xffffffffu, descs[dslot].mt_eff, 0);
+    const int units = __shfl_sync(0xffffffffu, descs[dslot].units, 0);
+    const uint32_t inv = __shfl_sync(0xffffffffu, descs[dslot].inv, 0);
+    if (++dslot == kDescSlots) dslot = 0;
     // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
     uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
     const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
 #pragma unroll
     for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
       int j, gi;
-      unit_split(w + i * kMmaWarps, it.mt_eff, inv, j, gi);
+      unit_split(w + i * kMmaWarps, mt_eff, inv, j, gi);
       b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
       a16[i] = b16[i] + (uint32_t) j * 8;
       dcol[i] = (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
     }
-    mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
-    mbar_wait_parked(bar_full + 8u * (uint32_t) stage, phase);
-    tc_fence_after_sync();
     if (elect_one()) {
       // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
       // outer loop, so consecutive instructions hit different accumulators
@@ -257,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     q8_dwconv3x3_umma_kernel(const __grid_constant__ DwTcParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ Ctl ctl;
+  __shared__ ItemDesc descs[kDescSlots];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
@@ -288,12 +319,25 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == kTmaWarp) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, dslot = 0;
       uint32_t phase = 0;
       ItemPos pos = first_pos(p, first);
       for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
         const DwItem it = make_item(p, pos);
         mbar_wait_relaxed(smem_u32(&ctl.empty[stage]), phase ^ 1, 32);
+        {  // the item's descriptor for the other roles (see ItemDesc)
+          ItemDesc d;
+          d.tile_base = reinterpret_cast<uint64_t>(p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w + it.ox0) * p.out_stride);
+          d.n0 = it.n0, d.oy0 = it.oy0, d.ox0 = it.ox0, d.c0 = it.cb * p.G * 16;
+          d.mt_eff = it.mt_eff, d.g_eff = it.g_eff;
+          d.inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
+          d.units = it.mt_eff * it.g_eff;
+          d.pad[0] = d.pad[1] = 0;
+          const uint4* s4 = reinterpret_cast<const uint4*>(&d);
+          uint4* d4 = reinterpret_cast<uint4*>(&descs[dslot]);
+          d4[0] = s4[0], d4[1] = s4[1], d4[2] = s4[2];
+          if (++dslot == kDescSlots) dslot = 0;
+        }
         const uint32_t bar = smem_u32(&ctl.full[stage]);
         const uint32_t dst0 = smem_base + (uint32_t) stage * p.stage_bytes;
         mbar_arrive_expect_tx(bar, (uint32_t) it.g_eff * (uint32_t) (p.planes * p.plane_tx + p.b_bytes));
@@ -320,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // concurrently (1 -> 4 warps: 2x faster; 4 -> 7: another 2-5 %); warp w owns the units w, w+7, ... of every item.
     // (ONE copy of the loop for all of them: per-warp template instances multiply the code and were measured 2.3x slower,
     // presumably instruction-cache misses)
-    mma_role<NB>(p, ctl, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
+    mma_role<NB>(p, ctl, descs, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
   } else {
     // ===================================== epilogue (16 warps) =====================================
     // Address and border-class arithmetic is split by how often it changes (the round-1 loop redid 64-bit pixel
@@ -336,19 +380,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     // few images, so 32 bits suffice (host-checked: nb * out_h * out_w * out_stride < 2^31)
     const uint32_t lane_off = (uint32_t) ((img * p.out_h + oyl) * p.out_w + px) * (uint32_t) p.out_stride;
     const uint32_t sub_step = 8u * (uint32_t) p.out_stride;  // one sub-tile (8 columns) further
-    int as = 0;
+    int as = 0, dslot = 0;
     uint32_t as_phase = 0;
-    ItemPos pos = first_pos(p, first);
     // values that depend on the SPATIAL tile only: with the contiguous schedule (channel block fastest) they change once
     // every `cblocks` items, so they are recomputed only then
-    uint8_t* tile_base = nullptr;   // warp-uniform origin of the spatial tile in the output tensor (channel 0)
     bool row_ok = false;
     uint32_t rm_row = 0;            // row class * 8 * channels: index of this lane's row of bias_cls, column class 0
-    for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
-      const DwItem it = make_item(p, pos);
-      const int c0 = it.cb * p.G * 16;
-      if (item == first || it.cb == 0) {
-        tile_base = p.out + ((size_t) ((long long) it.n0 * p.out_h + it.oy0) * p.out_w + it.ox0) * p.out_stride;
+    for (uint32_t item = first; item < total; item += step) {
+      const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
+      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
+      tc_fence_after_sync();
+      const ItemDesc it = load_desc(&descs[dslot]);  // the producer's decode of this item (see ItemDesc)
+      if (++dslot == kDescSlots) dslot = 0;
+      if (item == first || it.c0 == 0) {
         const int oy = it.oy0 + oyl;
         row_ok = img < p.nb && it.n0 + img < p.batch && oy < p.out_h;
         // row class: bit k set iff input row iy0 + k lies inside the image (taps below 0 / at or above in_h are padding)
@@ -357,16 +401,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t rm = rhi >= 3 ? 0u : (((7u << rlo) & 7u) & (7u >> rhi));
         rm_row = rm * 8u * (uint32_t) p.channels;
       }
-      uint8_t* const obase = tile_base + c0;
-      const uint32_t bias_row = rm_row + (uint32_t) c0;
-      const uint32_t empty_bar = smem_u32(&ctl.tmem_empty[as]);
-      mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
-      tc_fence_after_sync();
+      uint8_t* const obase = reinterpret_cast<uint8_t*>(it.tile_base) + it.c0;
+      const uint32_t bias_row = rm_row + (uint32_t) it.c0;
       const uint32_t tbase = tmem_base + (uint32_t) as * p.acc_stride + ((uint32_t) (q * 32) << 16);
       // warp (q, h) takes the units h, h+4, ... (unit = sub-tile j x channel group gi, j fastest); the per-sub-tile
       // values are redone only when j changes
-      const int units = it.mt_eff * it.g_eff;
-      const uint32_t inv = it.mt_eff == p.mt ? p.inv_g : p.inv_tail;
+      const int units = it.units;
+      const uint32_t inv = it.inv;
       if (h >= units) {  // nothing to read (narrow tail item)
         tc_fence_before_sync();
         mbar_arrive(empty_bar);
