@@ -395,19 +395,37 @@ __device__ __forceinline__ void load_a_conv_run9_raw(const IgemmParams& p, const
     if (hi >= 3) m0 = 0xFFFFFFFFu;
     const uint32_t base = ((int) cn == raw_n0 ? raw_b0 : raw_b1) + (uint32_t) (iy0 * row_pitch + ix0 * 3);
     uint32_t r[3][3];
+    // Interior pixels (all nine taps inside the image) are the rule — in the 224x224 stem only output column 0 and output
+    // row 0 touch padding — and need no masks at all.  The choice is made per WARP (a divergent branch would run both
+    // sides): measured on the round-2 kernel, the four loader warps were the stage every other role waited for, at ~3x the
+    // instructions per pixel of this path.
+    const bool interior = live && lo == 0 && hi == 0 && iy0 >= 0 && iy0 + 2 * p.dil_h < p.in_h;
+    if (__all_sync(0xffffffffu, interior)) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++) {
-      const int iy = iy0 + ky * p.dil_h;
-      const bool rowok = live && (unsigned) iy < (unsigned) p.in_h;
-      const uint32_t a = base + (uint32_t) (ky * p.dil_h * row_pitch);
-      uint32_t w[3];
-      run9_load_smem(rowok ? a : raw_safe, w);  // (any readable address when the row is padding)
-      const uint32_t sh = (a & 3u) * 8;
-      const uint32_t r0 = __funnelshift_r(w[0], w[1], sh), r1 = __funnelshift_r(w[1], w[2], sh), r2 = w[2] >> sh;
-      const uint32_t k0 = rowok ? m0 : 0xFFFFFFFFu, k1 = rowok ? m1 : 0xFFFFFFFFu, k2 = rowok ? m2 : 0xFFu;
-      r[ky][0] = (r0 & ~k0) | (fill & k0);
-      r[ky][1] = (r1 & ~k1) | (fill & k1);
-      r[ky][2] = ((r2 & ~k2) | (fill & k2)) & 0xFFu;
+      for (int ky = 0; ky < 3; ky++) {
+        const uint32_t a = base + (uint32_t) (ky * p.dil_h * row_pitch);
+        uint32_t w[3];
+        run9_load_smem(a, w);
+        const uint32_t shk = (a & 3u) * 8;
+        r[ky][0] = __funnelshift_r(w[0], w[1], shk);
+        r[ky][1] = __funnelshift_r(w[1], w[2], shk);
+        r[ky][2] = (w[2] >> shk) & 0xFFu;
+      }
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+        const int iy = iy0 + ky * p.dil_h;
+        const bool rowok = live && (unsigned) iy < (unsigned) p.in_h;
+        const uint32_t a = base + (uint32_t) (ky * p.dil_h * row_pitch);
+        uint32_t w[3];
+        run9_load_smem(rowok ? a : raw_safe, w);  // (any readable address when the row is padding)
+        const uint32_t sh = (a & 3u) * 8;
+        const uint32_t r0 = __funnelshift_r(w[0], w[1], sh), r1 = __funnelshift_r(w[1], w[2], sh), r2 = w[2] >> sh;
+        const uint32_t k0 = rowok ? m0 : 0xFFFFFFFFu, k1 = rowok ? m1 : 0xFFFFFFFFu, k2 = rowok ? m2 : 0xFFu;
+        r[ky][0] = (r0 & ~k0) | (fill & k0);
+        r[ky][1] = (r1 & ~k1) | (fill & k1);
+        r[ky][2] = ((r2 & ~k2) | (fill & k2)) & 0xFFu;
+      }
     }
     // K row: bytes [0,9) = ky 0, [9,18) = ky 1, [18,27) = ky 2, [27,32) = padding (zero weights)
     const uint32_t k0 = r[0][0], k1 = r[0][1];
@@ -845,34 +863,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     int stage = 0;
     uint32_t phase = 0;
-    // raw staging ring: buffer rb (use parity rpar) holds the rows of the current item; thread 0 keeps raw_bufs - 1
-    // items of rows in flight ahead of the one being transformed (a single outstanding copy was measured to leave the
-    // loader warps waiting ~95% of the time)
-    [[maybe_unused]] int rb = 0, pb = 0;           // consumer / producer buffer index
-    [[maybe_unused]] uint32_t rpar = 0, ppar = 0;  // their use parities
-    [[maybe_unused]] long long pitem = first;      // next item whose rows have not been requested yet
+    // raw staging ring: buffer rb (use parity rpar) holds the rows of the current item; they are requested by a thread of
+    // the store warp (see there), which keeps up to raw_bufs items of rows in flight
+    [[maybe_unused]] int rb = 0;
+    [[maybe_unused]] uint32_t rpar = 0;
     [[maybe_unused]] const uint32_t raw0 = smem_base + (uint32_t) p.smem_raw_off;
-    [[maybe_unused]] auto issue_raw = [&]() {  // thread 0: request the rows of `pitem` into buffer pb
-      const Item nx = decode_item(p, pitem);
-      RawSeg sg[2];
-      const int ns = raw_segments(p, nx, sg);
-      mbar_wait(smem_u32(&ctl.raw_empty[pb]), ppar ^ 1);
-      const uint32_t bar = smem_u32(&ctl.raw_full[pb]);
-      mbar_arrive_expect_tx(bar, sg[0].bytes + (ns > 1 ? sg[1].bytes : 0u));
-      for (int s = 0; s < ns; s++) {
-        // several medium copies instead of one large one: they proceed in parallel
-        for (uint32_t o = 0; o < sg[s].bytes; o += 4096) {
-          const uint32_t len = sg[s].bytes - o < 4096 ? sg[s].bytes - o : 4096;
-          bulk_g2s(raw0 + (uint32_t) pb * (uint32_t) p.raw_cap + sg[s].soff + o, sg[s].g + o, len, bar);
-        }
-      }
-      pitem += step;
-      if (++pb == p.raw_bufs) pb = 0, ppar ^= 1;
-    };
-    if constexpr (VEC == kVecRaw9) {
-      if (ltid == 0)
-        for (int i = 0; i < p.raw_bufs - 1 && pitem < p.total_items; i++) issue_raw();
-    }
     for (long long item = first; item < p.total_items; item += step) {
       const Item it = decode_item(p, item);
       for (int ks = 0; ks < p.k_stages; ks++) {
@@ -906,7 +901,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else if constexpr (VEC == 0) {
           load_a_conv_run9(p, it, a_stage, ltid);  // K = 27 fits one stage
         } else if constexpr (VEC == kVecRaw9) {
-          if (ltid == 0 && pitem < p.total_items) issue_raw();  // keep the ring of row requests full
           RawSeg sg[2];
           const int ns = raw_segments(p, it, sg);
           const uint32_t rbase = raw0 + (uint32_t) rb * (uint32_t) p.raw_cap;
@@ -1109,6 +1103,34 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp == kStoreWarp) {
     // ===================================== output stores =====================================
     const int pair = tid & 31;
+    if constexpr (VEC == kVecRaw9) {
+      if (pair == 2) {
+        // Raw-row producer of the 3x3x3 stem loader: requests the input rows of every item into the staging ring, as far
+        // ahead as the ring allows.  (Round 2: this used to be loader thread 0, in front of its own share of every item;
+        // decoding an item's row segments is ~400 serial instructions, and since a stage is complete only when all 128
+        // loader threads have arrived, that lane's detour was ~2 us per item for the whole pipeline — measured as the
+        // slope of the stem's time against its item count.)
+        const uint32_t raw0 = smem_base + (uint32_t) p.smem_raw_off;
+        int pb = 0;
+        uint32_t ppar = 0;
+        for (long long pitem = first; pitem < p.total_items; pitem += step) {
+          const Item nx = decode_item(p, pitem);
+          RawSeg sg[2];
+          const int ns = raw_segments(p, nx, sg);
+          mbar_wait_relaxed(smem_u32(&ctl.raw_empty[pb]), ppar ^ 1, 64);
+          const uint32_t bar = smem_u32(&ctl.raw_full[pb]);
+          mbar_arrive_expect_tx(bar, sg[0].bytes + (ns > 1 ? sg[1].bytes : 0u));
+          for (int s = 0; s < ns; s++) {
+            // several medium copies instead of one large one: they proceed in parallel
+            for (uint32_t o = 0; o < sg[s].bytes; o += 4096) {
+              const uint32_t len = sg[s].bytes - o < 4096 ? sg[s].bytes - o : 4096;
+              bulk_g2s(raw0 + (uint32_t) pb * (uint32_t) p.raw_cap + sg[s].soff + o, sg[s].g + o, len, bar);
+            }
+          }
+          if (++pb == p.raw_bufs) pb = 0, ppar ^= 1;
+        }
+      }
+    }
     if (pair < 2 && p.out_mode == 2) {
       // panel epilogue: every item (tails and ragged n-tiles included) leaves through 2-D tensor stores, one per panel
       // and box of rows; the TMA unit undoes the panel swizzle and clips rows >= M / columns >= N
