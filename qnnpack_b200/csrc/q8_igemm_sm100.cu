@@ -62,8 +62,8 @@ struct __align__(8) SmemCtl {
   uint64_t tmem_full[kMaxAccStages];
   uint64_t tmem_empty[kMaxAccStages];
   uint64_t b_full;
-  uint64_t out_full[2];  // epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
-  uint64_t out_free[2];  // store thread -> epilogue pair: the staging buffer may be overwritten
+  uint64_t out_full[4];  // [pair * 2 + buffer] epilogue pair -> store thread: the staged output tile is complete (256 arrivals)
+  uint64_t out_free[4];  // [pair * 2 + buffer] store thread -> epilogue pair: the staging buffer may be overwritten
   uint64_t raw_full[kMaxRawBufs];  // raw-row staging (3x3x3 stem loader): bulk copies landed / 128 loader threads done
   uint64_t raw_empty[kMaxRawBufs];
   uint32_t tmem_base;
@@ -811,8 +811,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     mbar_init(smem_u32(&ctl.b_full), kLoadThreads);
     for (int s = 0; s < 2; s++) {
-      mbar_init(smem_u32(&ctl.out_full[s]), kEpiPairThreads);
-      mbar_init(smem_u32(&ctl.out_free[s]), 1);
+      mbar_init(smem_u32(&ctl.out_full[2 * s]), kEpiPairThreads);
+      mbar_init(smem_u32(&ctl.out_free[2 * s]), 1);
+      mbar_init(smem_u32(&ctl.out_full[2 * s + 1]), kEpiPairThreads);
+      mbar_init(smem_u32(&ctl.out_free[2 * s + 1]), 1);
     }
     for (int s = 0; s < kMaxRawBufs; s++) {
       mbar_init(smem_u32(&ctl.raw_full[s]), 1);
@@ -1010,7 +1012,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int pair = warp >> 3;
     const int q = warp & 3, half = (warp >> 2) & 1;
     const int lane = tid & 31;
-    const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
+    // staging: one buffer per pair, or two used alternately (staging_bufs == 2, panel epilogue only) — with one, the pair's
+    // first staging write of an item waits until the tensor stores of its previous item have READ the buffer, which
+    // the round-2 profile of the 16 -> 96 expansion showed as 8 % of the epilogue warps' time
+    const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bufs * p.staging_bytes;
     mbar_wait(smem_u32(&ctl.b_full), 0);  // biases are in smem ("ones" mode reads them)
     if (p.out_mode == 2) {
       // panel epilogue: one specialised loop per (requantisation form, mode), chosen once per launch
@@ -1030,11 +1035,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           mbar_wait(smem_u32(&ctl.tmem_full[as]), as_phase);
           tc_fence_after_sync();
+          // buffer and the use count of that buffer's barriers (k-th item of the pair)
+          const uint32_t buf = p.staging_bufs == 2 ? (k & 1u) : 0u, use = p.staging_bufs == 2 ? (k >> 1) : k;
           epi2_item<RQ, FOLDED>(p, it.mt_eff, tmem_base + as * p.acc_stride + ((uint32_t) (q * 32) << 16),
-                                bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4, staging, row, half,
-                                smem_u32(&ctl.tmem_empty[as]), smem_u32(&ctl.out_free[pair]), (k & 1) ^ 1, p.n_tile);
+                                bias_smem + (uint32_t) ((it.g * p.n_tiles + it.nt) * p.n_tile) * 4,
+                                staging + buf * (uint32_t) p.staging_bytes, row, half, smem_u32(&ctl.tmem_empty[as]),
+                                smem_u32(&ctl.out_free[2 * pair + buf]), (use & 1) ^ 1, p.n_tile);
           fence_proxy_async_smem();  // staging writes (generic proxy) -> tensor stores (async proxy)
-          mbar_arrive(smem_u32(&ctl.out_full[pair]));
+          mbar_arrive(smem_u32(&ctl.out_full[2 * pair + buf]));
         }
       };
       using T5 = std::integral_constant<int, 5>;
@@ -1068,7 +1076,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       e.row = q * 32 + lane;
       e.n_valid = min(p.n_tile, p.goc - it.nt * p.n_tile);
       e.bulk = bulk;
-      e.out_free_bar = smem_u32(&ctl.out_free[pair]);
+      e.out_free_bar = smem_u32(&ctl.out_free[2 * pair]);
       e.out_free_parity = (k & 1) ^ 1;
       e.tmem_empty_bar = smem_u32(&ctl.tmem_empty[as]);
       // two specialised epilogues ("U" requantisation without / with clamp: every layer whose accumulators are bounded,
@@ -1080,7 +1088,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (p.out_mode == 1) {
         fence_proxy_async_smem();  // staging writes (generic proxy) -> bulk copy (async proxy)
-        mbar_arrive(smem_u32(&ctl.out_full[pair]));
+        mbar_arrive(smem_u32(&ctl.out_full[2 * pair]));
       }
     }
     }
@@ -1118,11 +1126,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (pair < 2 && p.out_mode == 2) {
       // panel epilogue: every item (tails and ragged n-tiles included) leaves through 2-D tensor stores, one per panel
       // and box of rows; the TMA unit undoes the panel swizzle and clips rows >= M / columns >= N
-      const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
+      const uint32_t staging0 = smem_base + p.smem_stage_off + pair * p.staging_bufs * p.staging_bytes;
       uint32_t k = 0;
       for (long long item = first + pair * step; item < p.total_items; item += 2 * step, k++) {
         const Item it = decode_item(p, item);
-        mbar_wait_relaxed(smem_u32(&ctl.out_full[pair]), k & 1, 20);
+        const uint32_t buf = p.staging_bufs == 2 ? (k & 1u) : 0u, use = p.staging_bufs == 2 ? (k >> 1) : k;
+        const uint32_t staging = staging0 + buf * (uint32_t) p.staging_bytes;
+        mbar_wait_relaxed(smem_u32(&ctl.out_full[2 * pair + buf]), use & 1, 20);
         const int rows = it.mt_eff * kTileM;
         if (p.e2_dense) {  // contiguous output rows: the whole item is one run of bytes
           const long long left = p.M - it.m0;
@@ -1137,22 +1147,29 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_store_2d(map, staging + (uint32_t) p.e2_off[pk] + (uint32_t) (r0 * p.e2_width[pk]), col, (int) (it.m0 + r0));
         }
         bulk_commit();
-        bulk_wait_read<0>();
-        mbar_arrive(smem_u32(&ctl.out_free[pair]));
+        // the buffer is handed back once its stores have read it; with two buffers the stores of THIS item may stay in
+        // flight while the pair fills the other one, so only the previous group has to be done
+        if (p.staging_bufs == 2) {
+          bulk_wait_read<1>();
+          if (k > 0) mbar_arrive(smem_u32(&ctl.out_free[2 * pair + (buf ^ 1u)]));
+        } else {
+          bulk_wait_read<0>();
+          mbar_arrive(smem_u32(&ctl.out_free[2 * pair]));
+        }
       }
       bulk_wait<0>();
     } else if (pair < 2 && p.out_mode == 1) {
-      const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bytes;
+      const uint32_t staging = smem_base + p.smem_stage_off + pair * p.staging_bufs * p.staging_bytes;
       uint32_t k = 0;
       for (long long item = first + pair * step; item < p.total_items; item += 2 * step, k++) {
         const Item it = decode_item(p, item);
-        mbar_wait_relaxed(smem_u32(&ctl.out_full[pair]), k & 1, 20);
+        mbar_wait_relaxed(smem_u32(&ctl.out_full[2 * pair]), k & 1, 20);
         if (it.m0 + (long long) it.mt_eff * kTileM <= p.M) {
           bulk_s2g(p.out + (size_t) it.m0 * p.out_stride, staging, (uint32_t) (it.mt_eff * kTileM * p.goc));
           bulk_commit();
           bulk_wait_read<0>();
         }
-        mbar_arrive(smem_u32(&ctl.out_free[pair]));
+        mbar_arrive(smem_u32(&ctl.out_free[2 * pair]));
       }
       bulk_wait<0>();
     }

@@ -985,6 +985,7 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       p.bias_count = (int) op->bias_count;
       p.smem_b_off = op->smem_b_off, p.smem_bias_off = op->smem_bias_off, p.smem_a_off = op->smem_a_off;
       p.smem_stage_off = op->smem_stage_off, p.staging_bytes = op->staging_bytes, p.smem_total = op->smem_total;
+      p.staging_bufs = 1;
       p.izp = op->izp, p.kzp = op->kzp;
       p.rq = op->rq;
       p.rq_mode = op->rq_mode;
@@ -1062,6 +1063,23 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
           !env_set("QNNP_CUDA_NO_TMA") && make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K, op->skc)) {
         vec = 32;
         pl.has_tmap_a = true;
+      }
+      // panel epilogue: a second staging buffer per epilogue pair when shared memory allows — the shallow-K layers (where the
+      // epilogue is the long pole) have far more ring stages than they can use, so stages beyond "3 items of K or 64 KB in
+      // flight" are traded for it
+      if (p.out_mode == 2 && vec != 2 && !env_set("QNNP_CUDA_SINGLE_STAGING")) {
+        const int limit = g_lib.max_smem_optin - kCtlReserve;
+        const int a_stage = p.mt * p.skc * q8::kChunkBytes;
+        auto total = [&](int st) { return (int) round_up((size_t) p.smem_a_off + (size_t) st * p.stage_bytes, 1024) + 4 * p.staging_bytes + 1024; };
+        auto enough = [&](int st) { return st >= 3 && ((long long) st * a_stage >= 64 * 1024 || st >= 3 * p.k_stages); };
+        int stages = p.num_stages;
+        while (total(stages) > limit && enough(stages - 1)) stages--;
+        if (total(stages) <= limit && (stages == p.num_stages || enough(stages))) {
+          p.num_stages = stages;
+          p.smem_stage_off = (int) round_up((size_t) p.smem_a_off + (size_t) stages * p.stage_bytes, 1024);
+          p.smem_total = total(stages);
+          p.staging_bufs = 2;
+        }
       }
       pl.grid = (int) persistent_grid(p.total_items);
       pl.ig = p;
