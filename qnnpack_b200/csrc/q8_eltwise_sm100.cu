@@ -4,8 +4,8 @@
 // Replaces (reference, paths relative to its root):
 //   add_nc_q8                     src/add.c:22-149,  ukernel src/q8vadd/sse2.c,  spec qnnp_add_quantize requantization.h:500-522
 //   global_average_pooling_nwc_q8 src/global-average-pooling.c:22-147, src/q8gavgpool/*, spec qnnp_avgpool_quantize :482-498
-//   average_pooling2d_nhwc_q8     src/average-pooling.c:36-290, src/q8avgpool/*  (same quantisation, padding reads izp)
-//   max_pooling2d_nhwc_u8         src/max-pooling.c:36-228, src/u8maxpool/*      (max over the taps inside the image, clamp)
+//   average_pooling2d_nhwc_q8     src/average-pooling.c:36-275, src/q8avgpool/*  (same quantisation, padding reads izp)
+//   max_pooling2d_nhwc_u8         src/max-pooling.c:36-223, src/u8maxpool/*      (max over the taps inside the image, clamp)
 //   clamp_nc_u8                   src/clamp.c, src/u8clamp/*
 //   sigmoid_nc_q8 / leaky_relu_nc_q8   src/sigmoid.c, src/leaky-relu.c -> 256-entry table, src/x8lut/scalar.c
 //   softargmax_nc_q8              src/softargmax.c, src/operator-run.c:625-637, src/u8rmax/*, src/u8lut32norm/scalar.c
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) q8_pool2d_kernel(const __grid_consta
       // src/indirection.c:218-224: a tap outside the image reads the nearest edge pixel (doz(), then min with size - 1)
       iy = iy < 0 ? 0 : (iy > p.in_h - 1 ? p.in_h - 1 : iy);
     } else if ((unsigned) iy >= (unsigned) p.in_h) {
-      continue;  // src/average-pooling.c:118-124: a padded tap reads the zero buffer = izp, i.e. contributes izp - izp = 0
+      continue;  // src/average-pooling.c:143-150: a padded tap reads the zero buffer = izp, i.e. contributes izp - izp = 0
     }
     for (int kx = 0; kx < p.kw; kx++) {
       int ix = ox * p.stride_w + kx * p.dil_w - p.pad_left;

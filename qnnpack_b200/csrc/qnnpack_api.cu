@@ -2026,7 +2026,7 @@ QNNP_EXPORT enum qnnp_status qnnp_setup_global_average_pooling_nwc_q8(qnnp_opera
   return finish_setup(op, batch_size * width, op->channels, batch_size, op->channels);
 }
 
-// ---- average / max pooling (src/average-pooling.c:36-290, src/max-pooling.c:36-228) --------------------------------------
+// ---- average / max pooling (src/average-pooling.c:36-275, src/max-pooling.c:36-223) --------------------------------------
 QNNP_EXPORT enum qnnp_status qnnp_create_average_pooling2d_nhwc_q8(
     uint32_t input_padding_top, uint32_t input_padding_right, uint32_t input_padding_bottom, uint32_t input_padding_left,
     uint32_t pooling_height, uint32_t pooling_width, uint32_t stride_height, uint32_t stride_width, size_t channels,
