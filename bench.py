@@ -249,6 +249,33 @@ def measure_tensor_bound_gemm(lib, torch, dev, peak_tops, m=65536, n=4096, k=409
             "rows_checked": rows, "mismatches": int(np.count_nonzero(got != want))}
 
 
+def measure_hbm_by_mix(torch, dev, nbytes=4 << 30, reps=5):
+    """HBM bandwidth by access mix, measured live with the device's own fill / copy engines' kernels (torch memset and
+    copy): a WRITE-ONLY stream tops out far below the read+write copy figure that MEASURED_PEAKS.json holds, which is what
+    bounds the write-heavy 1x1 expansions (6 bytes written per byte read)."""
+    x = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    y = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    w_ms = timed(lambda: x.zero_())
+    c_ms = timed(lambda: y.copy_(x))
+    del x, y
+    torch.cuda.empty_cache()
+    return {"write_only_gbs": nbytes / 1e6 / w_ms, "copy_gbs": 2 * nbytes / 1e6 / c_ms, "bytes": nbytes,
+            "how": "torch memset / device-to-device copy of 4 GiB, CUDA events"}
+
+
 def measure_small_batch_latency(lib, torch, dev, M, params, batches=(1, 32), iters=50):
     """QNNPACK's own regime: one or a few images.  The 53 asynchronous C-ABI runs of a step are captured once in a CUDA
     graph (launch-bound: ~53 kernels of a few microseconds each) and replayed; the un-captured loop is timed beside it."""
@@ -518,6 +545,7 @@ def b200_main(args, rank, local_rank, world):
             extras["int8_peak_sustained"] = {"tops": tops_s, "ms_per_launch": ms_s, "launches": 140, "clocks": sampler.stop()}
             extras["tensor_bound_gemm"] = measure_tensor_bound_gemm(lib, torch, dev, tops, peak_sustained=tops_s)
             if world == 1:
+                extras["hbm_by_mix"] = measure_hbm_by_mix(torch, dev)
                 extras["full_network"] = measure_full_network(lib, torch, dev, M, B, min(args.steps, 5), 2, measured_peaks()[0])
                 extras["small_batch_latency"] = measure_small_batch_latency(lib, torch, dev, M, params)
                 extras["e2e_plugin_host_pointers"] = measure_e2e_plugin(lib, M, params)
@@ -574,6 +602,20 @@ def b200_main(args, rank, local_rank, world):
                       "int8 tensor pipe can bind"}
     layers_out = [{"layer": l.name, "kind": l.kind, "ms": layer_ms[i], "gbs": l.algorithmic_bytes(B) / 1e6 / layer_ms[i],
                    "tops": l.ops(B) / 1e9 / layer_ms[i]} for i, l in enumerate(stack.layers)]
+    # Second reading of the roofline: a launch cannot finish before its OUTPUT has been written at the write-only rate
+    # either.  bound = max(all bytes / copy peak, output bytes / write-only peak); informative, `roofline` keeps the contract.
+    mixed = None
+    wo = (extras.get("hbm_by_mix") or {}).get("write_only_gbs")
+    if wo:
+        tot_bound = 0.0
+        for i, l in enumerate(stack.layers):
+            out_b = B * l.cout * (1 if l.kind == "fc" else l.out_h * l.out_h)
+            bound = max(l.algorithmic_bytes(B) / (peak_gbs * 1e6), out_b / (wo * 1e6))
+            layers_out[i]["mixed_bound_ms"] = bound
+            layers_out[i]["frac_of_mixed_bound"] = bound / layer_ms[i]
+            tot_bound += bound
+        mixed = {"write_only_gbs": wo, "stack_bound_ms": tot_bound, "stack_frac": tot_bound / ms_per_step,
+                 "note": "per launch max(bytes / copy peak, output bytes / write-only peak); see layers[].frac_of_mixed_bound"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -607,6 +649,7 @@ def b200_main(args, rank, local_rank, world):
         "roofline": roofline, "cpu_baseline": cpu, "q8gemm_sweep": q8gemm, "per_kernel": per_kernel, "layers": layers_out,
         "stack_ops_g": stack.total_ops(B) / 1e9, "stack_algorithmic_gb": stack.total_bytes(B) / 1e9,
         "stack_frac_of_hbm_roofline": (stack.total_bytes(B) / 1e6 / peak_gbs) / ms_per_step,
+        "stack_mixed_bound": mixed,
     }
     print(json.dumps(line), file=result_out, flush=True)
     faulthandler.cancel_dump_traceback_later()

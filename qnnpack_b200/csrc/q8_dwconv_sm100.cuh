@@ -36,7 +36,7 @@ struct DwStreamParams {
   int in_h, in_w, out_h, out_w;
   int stride, pad_top, pad_left;
   int cgroups, xstrips, ychunks, tyc;
-  int wmode;            // 0: one s8 operand, 1: one u8 operand (kzp == 0), 2: two s8 operands (w - kzp = A + B)
+  int wmode;            // 0: one s8 operand, 1: one u8 operand (kzp == 0), 2: two s8 operands (w - kzp = A + B), 3: one s8 operand holding kzp - w
   int izp;
   int rq_mode;
   int shift_mul;        // see requant_dev.cuh
@@ -69,7 +69,7 @@ struct DwTcParams {
   int nb_cols;              // accumulator columns per unit: 16, or 32 when w - kzp is split into two s8 operands
   int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
   int acc_stride, acc_stages;
-  int epi_poll_ns;          // back-off of the epilogue warps' accumulator poll (0 = spin)
+  int acc_sign;             // +1, or -1 when the B operand holds kzp - w (the accumulators are the negated sums)
   // item schedule: a CTA's next item is the NEXT item; in (cb, xtile, ytile, nblk) digits that is this step
   int chunk;                // items per CTA: CTA b runs items [b * chunk, min(total, (b + 1) * chunk))
   int step_cb, step_x, step_y, step_n;

@@ -113,14 +113,18 @@ __device__ __forceinline__ void accumulate_row(const uint32_t (&win)[TX][4], con
   }
 }
 
-template <int RQ>
+// NEG: the weight operand holds kzp - w (WMODE 3), so the slots hold the NEGATED accumulators (started from the negated bias)
+template <int RQ, bool NEG>
 __device__ __forceinline__ void finish_row(const DwStreamParams& p, uint8_t* obase, int oy, int oy_end, int ox0,
-                                           int32_t (&acc)[TX][4]) {
+                                           int32_t (&acc_in)[TX][4]) {
   if (oy >= 0 && oy < oy_end) {
     uint8_t* orow = obase + (size_t) oy * p.out_w * p.out_stride;
 #pragma unroll
     for (int x = 0; x < TX; x++) {
       if (ox0 + x < p.out_w) {
+        int32_t acc[TX][4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[x][c] = NEG ? -acc_in[x][c] : acc_in[x][c];
         uint32_t packed;
         if constexpr (RQ == 5 || RQ == 6) {
           auto rq1 = [&](int32_t nu) -> int32_t {
@@ -170,6 +174,8 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
   if constexpr (RQ == 5 || RQ == 6) {  // "U" requantisation consumes n + 2^31 (mod 2^32): the offset rides on the bias
     bias.x ^= 0x80000000, bias.y ^= 0x80000000, bias.z ^= 0x80000000, bias.w ^= 0x80000000;
   }
+  constexpr bool NEG = WMODE == 3;  // negated weight operand: accumulate -(bias + sum), negate once per output
+  if constexpr (NEG) bias.x = -bias.x, bias.y = -bias.y, bias.z = -bias.z, bias.w = -bias.w;
 
   uint8_t* obase = p.out + (size_t) n * p.out_h * p.out_w * p.out_stride + c0;
   const uint32_t fill = (uint32_t) p.izp * 0x01010101u;
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
           accumulate_row<WMODE, true>(win, wa[0], wb[0], acc[v], bias);
           accumulate_row<WMODE, false>(win, wa[1], wb[1], acc[(v + 2) % 3], bias);
           accumulate_row<WMODE, false>(win, wa[2], wb[2], acc[(v + 1) % 3], bias);
-          finish_row<RQ>(p, obase, t < 2 ? -1 : oy0 + t - 2, oy_end, ox0, acc[(v + 1) % 3]);
+          finish_row<RQ, NEG>(p, obase, t < 2 ? -1 : oy0 + t - 2, oy_end, ox0, acc[(v + 1) % 3]);
         }
       }
     }
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(128, 3) q8_dwconv3x3_stream_kernel(const __gri
             accumulate_row<WMODE, true>(win, wa[0], wb[0], acc[v >> 1], bias);
             accumulate_row<WMODE, false>(win, wa[2], wb[2], acc[1 - (v >> 1)], bias);
             const int o = (t >> 1) - 1;
-            finish_row<RQ>(p, obase, o < 0 ? -1 : oy0 + o, oy_end, ox0, acc[1 - (v >> 1)]);
+            finish_row<RQ, NEG>(p, obase, o < 0 ? -1 : oy0 + o, oy_end, ox0, acc[1 - (v >> 1)]);
           } else {
             accumulate_row<WMODE, false>(win, wa[1], wb[1], acc[v >> 1], bias);
           }
@@ -262,6 +268,7 @@ cudaError_t launch_wmode(const DwStreamParams& p, cudaStream_t stream) {
   switch (p.wmode) {
     case 0: return launch_rq<S, 0>(p, stream);
     case 1: return launch_rq<S, 1>(p, stream);
+    case 3: return launch_rq<S, 3>(p, stream);
     default: return launch_rq<S, 2>(p, stream);
   }
 }

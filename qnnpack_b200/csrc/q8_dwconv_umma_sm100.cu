@@ -202,7 +202,15 @@ __device__ __forceinline__ void epilogue_unit(const DwTcParams& p, uint32_t tadd
     const int32_t bb[4] = {b[t].x, b[t].y, b[t].z, b[t].w};
     int32_t n[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) n[i] = v[4 * t + i] + bb[i];  // for RQ 5/6 the table already carries the 2^31 offset of "U"
+    for (int i = 0; i < 4; i++) {  // (for RQ 5/6 the table already carries the 2^31 offset of "U")
+      if constexpr (NB == 32) {
+        n[i] = v[4 * t + i] + bb[i];
+      } else {
+        // one multiply-add: the sign of a negated weight operand (acc_sign = -1, see dw_tc_wmode) is free, and the add
+        // sits on the FMA pipe instead of the ALU pipe, which is the busier one in this epilogue
+        n[i] = v[4 * t + i] * p.acc_sign + bb[i];
+      }
+    }
     if constexpr (RQ == 5 || RQ == 6) {
       int32_t y[4];
 #pragma unroll

@@ -259,7 +259,17 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   const int umax = 256 / p->nb_cols;  // 8 (split operands) or 16 units
   const int smem_max = smem_optin - kCtlReserve - 1024;
   p->b_bytes = q8::kDwTcTaps * 2 * p->nb_cols * 16;
-  for (int cap = umax / 2 < 8 ? umax / 2 : 8; cap >= 1 && p->mt == 0; cap--) {
+  // QNNP_CUDA_DW_MT / QNNP_CUDA_DW_G: A/B overrides of the tile search (measurement only)
+  const int env_mt = getenv("QNNP_CUDA_DW_MT") != nullptr ? atoi(getenv("QNNP_CUDA_DW_MT")) : 0;
+  const int env_g = getenv("QNNP_CUDA_DW_G") != nullptr ? atoi(getenv("QNNP_CUDA_DW_G")) : 0;
+  // widest tile tried first.  Measured with 16 units per item (single weight operand), batch 4096: four sub-tiles x four
+  // channel groups beat seven x two wherever the layer has >= 4 channel groups (56x56x144: 1.69 vs 2.01 ms — with four
+  // sub-tiles an epilogue warp's units, 4 apart, all lie in the same sub-tile, so its column class is computed once per
+  // item), while a 2-group layer needs the wide tile to fill the accumulator stage at all (112x112x32: 1.03 vs 1.19 ms)
+  int cap0 = umax / 2 < 8 ? umax / 2 : 8;
+  if (umax == 16 && p->cgs >= 4) cap0 = 4;
+  if (env_mt >= 1 && env_mt <= cap0) cap0 = env_mt;
+  for (int cap = cap0; cap >= 1 && p->mt == 0; cap--) {
     const int xt = (nsub + cap - 1) / cap;
     const int mt = (nsub + xt - 1) / xt;
     const int box_px = 8 * mt + xoff_max;
@@ -269,6 +279,7 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
     const int a_bytes = p->planes * plane_bytes;
     const int cg_bytes = (int) round_up(a_bytes + p->b_bytes, 128);
     int G = umax / mt;
+    if (env_g >= 1 && env_g < G) G = env_g;
     if (G > q8::kDwTcMaxG) G = q8::kDwTcMaxG;
     if (G > p->cgs) G = p->cgs;
     for (; G >= 1; G = (G > 2 ? G - 1 : G - 1)) {
@@ -380,7 +391,8 @@ struct qnnp_operator {
   int c_pad = 0;  // dw
   uint32_t* d_dw_wa = nullptr;  // dw streaming kernel: packed taps, operands A and B
   uint32_t* d_dw_wb = nullptr;
-  int dw_wmode = 0;
+  int dw_wmode = 0;    // streaming depthwise kernel: 0 one s8 operand, 1 u8 (kzp == 0), 2 two s8 operands
+  int dwtc_wmode = 0;  // tensor-core depthwise kernel: dw_tc_wmode()
   uint8_t* d_dwtc_w = nullptr;     // dw tensor-core kernel: block-diagonal B operands (null if channels % 16 != 0)
   int32_t* d_dwtc_bias = nullptr;  // dw tensor-core kernel: [64 border classes][channels]
 
@@ -728,8 +740,27 @@ enum qnnp_status plan_and_pack_igemm(qnnp_operator* op, const uint8_t* kernel, c
   return map_cuda(e, "uploading packed weights");
 }
 
+// Weight-operand mode of the depthwise tensor-core kernel.  d = w - kzp spans 9 bits in general:
+//   1: kzp == 0                  -> raw u8 weights
+//   0: every d in [-128, 127]    -> one s8 operand holding d
+//   3: every -d in [-128, 127]   -> one s8 operand holding kzp - w; the accumulators are the NEGATED sums and the epilogue
+//                                   subtracts them (free: the bias add becomes a multiply-add by -1).  kzp = 127 — the
+//                                   reference benchmarks' own choice — always lands here: d in [-127, 128].
+//   2: otherwise                 -> two s8 operands d = floor(d/2) + ceil(d/2) side by side (32 accumulator columns per
+//                                   16 channels, added in the epilogue)
+int dw_tc_wmode(size_t C, const uint8_t* kernel, int kzp) {
+  if (kzp == 0) return 1;
+  bool fits = true, fits_neg = true;
+  for (size_t i = 0; i < C * 9; i++) {
+    const int d = (int) kernel[i] - kzp;
+    if (d < -128 || d > 127) fits = false;
+    if (-d < -128 || -d > 127) fits_neg = false;
+  }
+  return fits ? 0 : (fits_neg ? 3 : 2);
+}
+
 // Operands of the depthwise tensor-core kernel, built in HOST memory (tests/test_dw_umma_plan.py replays the kernel on
-// exactly these bytes).  kernel = [C][9] uint8, wmode: 0 one s8 operand, 1 u8 operand (kzp == 0), 2 two s8 operands.
+// exactly these bytes).  kernel = [C][9] uint8, wmode: see dw_tc_wmode().
 //   wp: per 16-channel group and UMMA u the B operand [2 K-chunks][nbc rows][16 B], each K-chunk diag(w_tap - kzp)
 //   bc: [64 border classes][C]: bias - izp * (sum of w - kzp over the taps inside the image); uform: XOR 2^31 (the offset
 //       of the "U" requantisation rides on the bias add)
@@ -747,7 +778,7 @@ void pack_dw_umma_host(size_t C, const uint8_t* kernel, const int32_t* bias, int
         for (int n = 0; n < 16; n++) {
           const int32_t w = kernel[(cg * 16 + n) * 9 + tap];
           const int32_t d = w - kzp;
-          int32_t da = wmode == 1 ? w : d, db = 0;
+          int32_t da = wmode == 1 ? w : (wmode == 3 ? -d : d), db = 0;
           if (wmode == 2) da = d >> 1, db = d - da;
           uint8_t* blk = wp.data() + (cg * q8::kDwTcTaps + u) * ub + (size_t) ch * nbc * 16;
           blk[(size_t) n * 16 + n] = (uint8_t) da;                        // B[n][k = n] of this K-chunk
@@ -771,27 +802,30 @@ enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int3
   const size_t C = op->groups;
   op->c_pad = (int) round_up(C, 4);
   std::vector<int32_t> w32((size_t) 9 * op->c_pad, 0), fbias(op->c_pad, 0);
-  bool fits_s8 = true;
+  bool fits_s8 = true, fits_neg = true;
   for (size_t c = 0; c < C; c++) {
     for (int t = 0; t < 9; t++) {
       const int32_t d = (int32_t) kernel[c * 9 + t] - (int32_t) op->kzp;
       w32[(size_t) t * op->c_pad + c] = d;
       if (d < -128 || d > 127) fits_s8 = false;
+      if (d < -127 || d > 128) fits_neg = false;
     }
     fbias[c] = fold_bias(bias[c], 9, op->izp, op->kzp, kernel + c * 9);
   }
   // streaming dp4a kernel: per channel and kernel row one word (tap kx=0, kx=1, kx=2, 0).
   //   kzp == 0            -> u8 weights as they are                      (wmode 1)
   //   every w-kzp in s8   -> one s8 operand                               (wmode 0)
+  //   every kzp-w in s8   -> one s8 operand holding kzp - w; the kernel accumulates the negated sums from the negated
+  //                          bias and negates once per output (wmode 3; kzp = 127, the reference benchmarks' choice)
   //   otherwise           -> w - kzp = A + B, A = floor(d/2), B = d - A   (wmode 2; both in [-128, 127] since kzp >= 1)
-  op->dw_wmode = op->kzp == 0 ? 1 : (fits_s8 ? 0 : 2);
+  op->dw_wmode = op->kzp == 0 ? 1 : (fits_s8 ? 0 : (fits_neg ? 3 : 2));
   std::vector<uint32_t> wa((size_t) 3 * op->c_pad, 0), wb((size_t) 3 * op->c_pad, 0);
   for (size_t c = 0; c < C; c++)
     for (int ky = 0; ky < 3; ky++) {
       uint32_t a = 0, b = 0;
       for (int kx = 0; kx < 3; kx++) {
         const int32_t d = w32[(size_t) (ky * 3 + kx) * op->c_pad + c];
-        int32_t da = d, db = 0;
+        int32_t da = op->dw_wmode == 3 ? -d : d, db = 0;
         if (op->dw_wmode == 2) {
           da = d >> 1;  // floor
           db = d - da;
@@ -816,7 +850,8 @@ enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int3
   if (e == cudaSuccess && (C % 16) == 0) {
     std::vector<uint8_t> wp;
     std::vector<int32_t> bc;
-    pack_dw_umma_host(C, kernel, bias, op->izp, op->kzp, op->dw_wmode, op->rq_mode == 5 || op->rq_mode == 6, wp, bc);
+    op->dwtc_wmode = dw_tc_wmode(C, kernel, op->kzp);
+    pack_dw_umma_host(C, kernel, bias, op->izp, op->kzp, op->dwtc_wmode, op->rq_mode == 5 || op->rq_mode == 6, wp, bc);
     e = cudaMalloc((void**) &op->d_dwtc_w, wp.size());
     if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_dwtc_bias, bc.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_w, wp.data(), wp.size(), cudaMemcpyHostToDevice);
@@ -1141,14 +1176,14 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && !env_set("QNNP_CUDA_DW_NO_UMMA") && (force_tc || !s2_rows) &&
           ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
           plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
-                       (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dw_wmode, g_lib.max_smem_optin, &tp) &&
+                       (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dwtc_wmode, g_lib.max_smem_optin, &tp) &&
           make_tmap_dw(&pl.dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
                        tp.box_rows, tp.nb);
       if (tc_ok) {
         tp.out = out, tp.wpack = op->d_dwtc_w, tp.bias_cls = op->d_dwtc_bias;
         tp.out_stride = (long long) op->out_stride;
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
-        if (const char* ev = getenv("QNNP_CUDA_DW_POLL_NS")) tp.epi_poll_ns = atoi(ev);
+        tp.acc_sign = op->dwtc_wmode == 3 ? -1 : 1;
         long long grid = persistent_grid(tp.total_items);
         tp.chunk = (int) ((tp.total_items + grid - 1) / grid);         // contiguous run of items per CTA
         grid = (tp.total_items + tp.chunk - 1) / tp.chunk;             // (CTAs that would start beyond the end are not launched)
@@ -1726,12 +1761,7 @@ QNNP_EXPORT int qnnp_cuda_debug_pack_dwconv(size_t channels, uint8_t input_zero_
                                             const uint8_t* kernel, const int32_t* bias, int u_form, uint8_t* wpack,
                                             int32_t* bias_cls) {
   if (channels == 0 || (channels % 16) != 0) return -1;
-  bool fits_s8 = true;
-  for (size_t i = 0; i < channels * 9; i++) {
-    const int d = (int) kernel[i] - (int) kernel_zero_point;
-    if (d < -128 || d > 127) fits_s8 = false;
-  }
-  const int wmode = kernel_zero_point == 0 ? 1 : (fits_s8 ? 0 : 2);
+  const int wmode = dw_tc_wmode(channels, kernel, kernel_zero_point);
   std::vector<uint8_t> wp;
   std::vector<int32_t> bc;
   pack_dw_umma_host(channels, kernel, bias, input_zero_point, kernel_zero_point, wmode, u_form != 0, wp, bc);

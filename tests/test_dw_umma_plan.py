@@ -192,7 +192,7 @@ def test_ineligible_shapes_fall_back(plan):
     assert plan(16, 1, 9, 9, 2)[0] is None      # stride 2 needs an even width
 
 
-def replay_packed(d, x, wpack, bias_cls, signed_b, s, pad, oh, ow):
+def replay_packed(d, x, wpack, bias_cls, signed_b, s, pad, oh, ow, acc_sign=1):
     """Like replay(), but with the library's own packed operands: every UMMA multiplies the two 16-byte K-chunks the
     descriptors address (the empty tap slot included: its LBO is 0 and its weights must be zero) with the B block
     [2 chunks][nb_cols rows][16 B] of (channel group, u); the epilogue adds the two operand halves and bias_cls."""
@@ -242,7 +242,7 @@ def replay_packed(d, x, wpack, bias_cls, signed_b, s, pad, oh, ow):
                     rm = sum(1 << ky for ky in range(3) if 0 <= iy0 + ky < h)
                     cm = sum(1 << kx for kx in range(3) if 0 <= ix0 + kx < w)
                     v = a[m, :16] + (a[m, 16:32] if nbc == 32 else 0)
-                    acc[nn, oy, ox, cg * 16:cg * 16 + 16] = v + bias_cls[rm * 8 + cm, cg * 16:cg * 16 + 16]
+                    acc[nn, oy, ox, cg * 16:cg * 16 + 16] = acc_sign * v + bias_cls[rm * 8 + cm, cg * 16:cg * 16 + 16]
     return acc
 
 
@@ -266,12 +266,13 @@ def test_kernel_replay_on_the_packed_operands(plan, c, n, h, w, s, pad, kzp, izp
     wmode = lib.qnnp_cuda_debug_pack_dwconv(c, izp, kzp, wk.ctypes.data, bias.ctypes.data, 0, wpack.ctypes.data,
                                             bias_cls.ctypes.data)
     dmin, dmax = int(wk.min()) - kzp, int(wk.max()) - kzp
-    assert wmode == (1 if kzp == 0 else 0 if (dmin >= -128 and dmax <= 127) else 2)
+    # 0: w - kzp fits s8; 3: kzp - w fits s8 (negated operand, e.g. kzp = 127: d in [-127, 128]); 2: two operands
+    assert wmode == (1 if kzp == 0 else 0 if (dmin >= -128 and dmax <= 127) else 3 if (-dmax >= -128 and -dmin <= 127) else 2)
     oh, ow = (h + 2 * pad[0] - 3) // s + 1, (w + 2 * pad[1] - 3) // s + 1
     d = plan(c, n, h, w, s, pad, wmode)[0]
     assert d is not None and d["nb_cols"] == (32 if wmode == 2 else 16) and d["b_signed"] == (0 if wmode == 1 else 1)
     x = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
-    got = replay_packed(d, x, wpack, bias_cls.astype(np.int64), wmode != 1, s, pad, oh, ow)
+    got = replay_packed(d, x, wpack, bias_cls.astype(np.int64), wmode != 1, s, pad, oh, ow, acc_sign=-1 if wmode == 3 else 1)
     assert np.array_equal(got, direct(x, wk, bias.astype(np.int64), izp, kzp, s, pad, oh, ow))
     # the "U" requantisation offset rides on the same table
     bias_u = np.zeros((64, c), dtype=np.int32)
