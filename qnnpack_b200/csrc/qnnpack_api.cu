@@ -1167,11 +1167,13 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       const bool stream_ok = cv == 4 && op->dil_h == 1 && op->dil_w == 1 && op->stride_h == op->stride_w &&
           (op->stride_h == 1 || op->stride_h == 2) && !env_set("QNNP_CUDA_DW_GENERIC");
       // tensor-core path: channels % 16 == 0 and 16-byte aligned pixels (TMA boxes, 16-byte output stores)
-      // (measured on MobileNetV2 at batch 4096: the tcgen05 kernel wins everywhere except stride-2 layers tiled by rows,
-      // where one channel group per item fits and the CUDA-core streaming kernel is ~8% faster; QNNP_CUDA_DW_UMMA=1
-      // forces the tensor-core path for every eligible shape, QNNP_CUDA_DW_NO_UMMA=1 disables it)
+      // (measured on MobileNetV2 at batch 4096: the tcgen05 kernel wins everywhere except — with the TWO-operand weight form
+      // only — stride-2 layers tiled by rows, where the CUDA-core streaming kernel is ~8% faster; with a single operand
+      // (16 accumulator columns per unit) it wins there too: 112x112x96 stride 2 1.87 vs 2.00 ms.  QNNP_CUDA_DW_UMMA=1 /
+      // QNNP_CUDA_DW_S2_UMMA=1 force the tensor-core path, QNNP_CUDA_DW_S2_STREAM=1 / QNNP_CUDA_DW_NO_UMMA=1 the other way)
       const bool force_tc = env_set("QNNP_CUDA_DW_UMMA");
-      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32 && !env_set("QNNP_CUDA_DW_S2_UMMA");
+      const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32 && !env_set("QNNP_CUDA_DW_S2_UMMA") &&
+          (op->dwtc_wmode == 2 || env_set("QNNP_CUDA_DW_S2_STREAM"));
       q8::DwTcParams& tp = pl.tp;
       const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && !env_set("QNNP_CUDA_DW_NO_UMMA") && (force_tc || !s2_rows) &&
           ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
