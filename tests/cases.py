@@ -233,6 +233,14 @@ DW_TC_CASES = [
     conv_case("tc_c32_s2_28_b3", 3, 28, 28, 32, 1, 1, stride=(2, 2), **DW_TC),
     conv_case("tc_c16_s2_18x6_nopad_b3", 3, 18, 6, 16, 1, 1, ks=(3, 3), stride=(2, 2)),
     conv_case("tc_c32_12x12_b5", 5, 12, 12, 32, 1, 1, **DW_TC),
+    # round 2: kzp = 127 (the default above) now takes the single NEGATED operand (kzp - w fits s8); these keep the
+    # two-operand form (32 accumulator columns per unit) covered on every geometry class, and the plain single operand at 128
+    conv_case("tc_c32_rows_kzp60_two_operands", 1, 20, 23, 32, 1, 1, kzp=60, **DW_TC),
+    conv_case("tc_c48_7x7_stack2_kzp200_two_operands", 3, 7, 7, 48, 1, 1, kzp=200, **DW_TC),
+    conv_case("tc_c32_s2_rows_kzp90_two_operands", 1, 40, 36, 32, 1, 1, stride=(2, 2), kzp=90, **DW_TC),
+    conv_case("tc_c64_56_kzp1_two_operands", 2, 56, 56, 64, 1, 1, kzp=1, **DW_TC),
+    conv_case("tc_c32_s2_rows_kzp128", 1, 40, 36, 32, 1, 1, stride=(2, 2), kzp=128, **DW_TC),
+    conv_case("tc_c144_56_b2_negated", 2, 56, 56, 144, 1, 1, **DW_TC),
 ]
 
 STEM_CASES = [
