@@ -69,6 +69,8 @@ struct DwTcParams {
   int nb_cols;              // accumulator columns per unit: 16, or 32 when w - kzp is split into two s8 operands
   int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
   int acc_stride, acc_stages;
+  int store32;              // 1: the epilogue pairs channel groups and writes 32 bytes per pixel with one 256-bit store
+                            // (needs 32-byte aligned output pixels and an even number of channel groups per item)
   int acc_sign;             // +1, or -1 when the B operand holds kzp - w (the accumulators are the negated sums)
   // item schedule: a CTA's next item is the NEXT item; in (cb, xtile, ytile, nblk) digits that is this step
   int chunk;                // items per CTA: CTA b runs items [b * chunk, min(total, (b + 1) * chunk))

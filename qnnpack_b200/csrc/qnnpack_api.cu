@@ -1186,6 +1186,7 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
         tp.out_stride = (long long) op->out_stride;
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
         tp.acc_sign = op->dwtc_wmode == 3 ? -1 : 1;
+        tp.store32 = (tp.G % 2) == 0 && !env_set("QNNP_CUDA_DW_STORE16");
         long long grid = persistent_grid(tp.total_items);
         tp.chunk = (int) ((tp.total_items + grid - 1) / grid);         // contiguous run of items per CTA
         grid = (tp.total_items + tp.chunk - 1) / tp.chunk;             // (CTAs that would start beyond the end are not launched)
