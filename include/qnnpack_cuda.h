@@ -65,7 +65,7 @@ int qnnp_cuda_debug_pack_igemm(size_t k, size_t n, uint8_t input_zero_point, uin
                                size_t* bias_count);
 
 /* Tiling of the depthwise tensor-core kernel (q8_dwconv_umma_sm100.cu) for a geometry; needs no GPU.  wmode: 0 = every
- * w - kzp fits s8, 1 = kzp == 0 (u8 weights), 2 = w - kzp split into two s8 operands.
+ * w - kzp fits s8, 1 = kzp == 0 (u8 weights), 2 = w - kzp split into two s8 operands, 3 = every kzp - w fits s8 (negated operand).
  * out = {G, mt, xt, yt, nt, nb, Q, whole, planes, box_rows, box_px, plane_tx, plane_bytes, a_bytes, b_bytes, cg_bytes,
  *        stage_bytes, num_stages, smem_total, x_org[2], a_off[5], a_lbo[5], sbo, nb_cols, b_signed, acc_stride, cblocks, cgs,
  *        total_items, 0, 0}.  Returns 1, or 0 when the shape is not eligible (the CUDA-core depthwise kernels run instead). */
@@ -77,6 +77,14 @@ int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, int in_w, int
  * Returns the weight-operand mode (0: one s8 operand, 1: u8, 2: two s8 operands) or -1. */
 int qnnp_cuda_debug_pack_dwconv(size_t channels, uint8_t input_zero_point, uint8_t kernel_zero_point, const uint8_t* kernel,
                                 const int32_t* bias, int u_form, uint8_t* wpack, int32_t* bias_cls);
+/* The same for the kernel's channel-PAIR form (32 channels per TMA box / UMMA, SWIZZLE_32B tiles; single weight operand only).
+ * plan: out[0..37] as above (a_off / a_lbo zero), out[38] = 1, out[39..47] = byte offset of tap ky*3+kx inside a pair's A block.
+ * pack: wpack receives ceil(channels / 32) * 9 * 1024 bytes: per pair and tap a K-major block [2 K-chunks][32 rows][16 B] =
+ * diag(w - kzp), or kzp - w when the returned mode is 3, or raw w when it is 1; returns -1 when the weights need two operands.
+ * wmode of both calls: 0, 1 as above, 3 = one s8 operand holding kzp - w (accumulators negated). */
+int qnnp_cuda_debug_plan_dwconv32(int channels, int batch, int in_h, int in_w, int out_h, int out_w, int stride, int pad_top,
+                                  int pad_left, int wmode, int out[48]);
+int qnnp_cuda_debug_pack_dwconv32(size_t channels, uint8_t kernel_zero_point, const uint8_t* kernel, uint8_t* wpack);
 /* Launches of the depthwise tensor-core kernel since qnnp_initialize() (tests use it to prove the routing). */
 unsigned long long qnnp_cuda_debug_dw_umma_launch_count(void);
 

@@ -44,7 +44,8 @@ struct DwStreamParams {
 };
 
 // tcgen05 depthwise kernel (q8_dwconv_umma_sm100.cu): 3x3 depthwise as block-diagonal UMMAs over TMA-staged tiles
-constexpr int kDwTcTaps = 5;        // UMMAs (K = 32 = two taps) per (sub-tile, channel group): 9 taps + 1 empty slot
+constexpr int kDwTcTaps = 5;
+constexpr int kDwTcTaps32 = 9;      // pair mode: one UMMA (K = 32 channels) per tap        // UMMAs (K = 32 = two taps) per (sub-tile, channel group): 9 taps + 1 empty slot
 constexpr int kDwTcMaxStages = 8;
 constexpr int kDwTcMaxG = 8;        // channel groups (16 channels each) per work item
 
@@ -69,6 +70,10 @@ struct DwTcParams {
   int nb_cols;              // accumulator columns per unit: 16, or 32 when w - kzp is split into two s8 operands
   int b_signed;             // B operand format: 1 = s8, 0 = u8 (kzp == 0)
   int acc_stride, acc_stages;
+  int pair;                 // 1: channel PAIR mode — TMA boxes, smem pixels and UMMAs are 32 channels wide (32-byte sector granularity
+                            // on the L2, SWIZZLE_32B tiles, one K = 32 UMMA per tap with a 32x32 diagonal B, N = 32); cg_bytes,
+                            // plane_* and sbo then describe 32-byte pixels and one block per channel pair
+  int a_off9[9];            // pair mode: byte offset of tap (ky, kx) = index ky*3+kx inside a pair's A block
   int store32;              // 1: the epilogue pairs channel groups and writes 32 bytes per pixel with one 256-bit store
                             // (needs 32-byte aligned output pixels and an even number of channel groups per item)
   int acc_sign;             // +1, or -1 when the B operand holds kzp - w (the accumulators are the negated sums)

@@ -244,6 +244,66 @@ __device__ __forceinline__ void store32(uint8_t* dst, const uint4& lo, const uin
 // lane issues.  (Round 1 put the loop under `if (lane == 0)`: nvcc then rebuilt every operand in vector registers and
 // moved it across with an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, ~30 instructions per UMMA — 17 % of all the
 // instructions this kernel executed, profiles/r1h_dwconv_umma_first2.)
+// Channel-pair form (DwTcParams::pair): a pixel is 32 bytes (two channel groups) in a SWIZZLE_32B tile, one UMMA per tap
+// with K = 32 channels and a 32x32 diagonal B (N = 32: both groups' accumulators side by side).  The A descriptor's start
+// address is the tap's pixel — any multiple of 32 bytes: the swizzle is a function of the absolute shared-memory address
+// on both the TMA's and the tensor core's side (tools/microbench/sw32_probe.cu), base offset 0.
+__device__ __forceinline__ void mma_role_pair(const DwTcParams& p, Ctl& ctl, const ItemDesc* descs, uint32_t smem_base_v,
+                                              uint32_t tmem_base_v, int w_v, uint32_t first, uint32_t step, uint32_t total) {
+  const int w = __shfl_sync(0xffffffffu, w_v, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base_v, 0);
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_base_v, 0);
+  const uint32_t ctl_u = __shfl_sync(0xffffffffu, smem_u32(&ctl), 0);
+  const uint32_t bar_full = ctl_u + (uint32_t) offsetof(Ctl, full), bar_empty = ctl_u + (uint32_t) offsetof(Ctl, empty);
+  const uint32_t bar_tfull = ctl_u + (uint32_t) offsetof(Ctl, tmem_full), bar_tempty = ctl_u + (uint32_t) offsetof(Ctl, tmem_empty);
+  const uint32_t idesc = umma_idesc_i8(128, 32, false, p.b_signed != 0);
+  // A: K-major SWIZZLE_32B (layout type 6), rows of 32 bytes, SBO = one output row down; B: K-major no swizzle,
+  // [2 K-chunks][32 rows][16 B] per tap (LBO = 512 between the chunks, SBO = 128 between 8-row groups)
+  const uint32_t ahi = (((uint32_t) p.sbo >> 4) & 0x3FFFu) | (1u << 14) | (6u << 29);
+  const uint32_t bhi = (uint32_t) (umma_desc_kmajor_noswizzle(0, 0, 128) >> 32);
+  uint32_t alo[kDwTcTaps32], blo[kDwTcTaps32];
+#pragma unroll
+  for (int t = 0; t < kDwTcTaps32; t++) {
+    alo[t] = (((smem_base + (uint32_t) p.a_off9[t]) >> 4) & 0x3FFFu) | (1u << 16);
+    blo[t] = (uint32_t) umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) t * 1024u, 512, 0);
+  }
+  int stage = 0, as = 0, dslot = 0;
+  uint32_t phase = 0, as_phase = 0;
+  for (uint32_t item = first; item < total; item += step) {
+    mbar_wait_parked(bar_full + 8u * (uint32_t) stage, phase);
+    const int mt_eff = __shfl_sync(0xffffffffu, descs[dslot].mt_eff, 0);
+    const int g_eff = __shfl_sync(0xffffffffu, descs[dslot].g_eff, 0);
+    const uint32_t inv = __shfl_sync(0xffffffffu, descs[dslot].inv, 0);
+    if (++dslot == kDescSlots) dslot = 0;
+    const int units = mt_eff * ((g_eff + 1) >> 1);  // (sub-tile, channel pair), sub-tile fastest
+    const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
+    const uint32_t acc0 = tmem_u + (uint32_t) as * p.acc_stride;
+    mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
+    tc_fence_after_sync();
+    if (elect_one()) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {  // at most 8 units per item over 7 warps
+        const int un = w + i * kMmaWarps;
+        if (un >= units) break;
+        int j, gp;
+        unit_split(un, mt_eff, inv, j, gp);
+        const uint32_t b16 = st16 + (((uint32_t) gp * p.cg_bytes) >> 4);  // operand offsets in 16-byte units
+        const uint32_t a16 = b16 + (uint32_t) j * 16;                      // 8 pixels x 32 bytes per sub-tile
+        const uint32_t dcol = acc0 + (uint32_t) (gp * p.mt + j) * 32;
+#pragma unroll
+        for (int t = 0; t < kDwTcTaps32; t++)
+          umma_i8(dcol, pack_u64(alo[t] + a16, ahi), pack_u64(blo[t] + b16, bhi), idesc, t > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_empty + 8u * (uint32_t) stage);
+      umma_commit(bar_tfull + 8u * (uint32_t) as);
+    }
+    __syncwarp();
+    if (++stage == p.num_stages) stage = 0, phase ^= 1;
+    as ^= 1;
+    if (as == 0) as_phase ^= 1;
+  }
+}
+
 template <int NB>
 __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const ItemDesc* descs, uint32_t smem_base_v,
                                          uint32_t tmem_base_v, int w_v, uint32_t first, uint32_t step, uint32_t total) {
@@ -311,7 +371,7 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const It
   }
 }
 
-template <int S, int RQ, int NB>
+template <int S, int RQ, int NB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     q8_dwconv3x3_umma_kernel(const __grid_constant__ DwTcParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -369,16 +429,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         const uint32_t bar = smem_u32(&ctl.full[stage]);
         const uint32_t dst0 = smem_base + (uint32_t) stage * p.stage_bytes;
-        mbar_arrive_expect_tx(bar, (uint32_t) it.g_eff * (uint32_t) (p.planes * p.plane_tx + p.b_bytes));
         const int y0 = (p.whole ? 0 : it.oy0 * S) - p.pad_top;
-        for (int gi = 0; gi < it.g_eff; gi++) {
-          const int cg = it.cb * p.G + gi;
+        // one box per channel group (16 bytes per pixel) or, in pair mode, per channel PAIR (32 bytes per pixel: every
+        // 32-byte sector of the input is requested once instead of twice); channels beyond C are zero-filled by the TMA
+        const int blocks = PAIR ? (it.g_eff + 1) >> 1 : it.g_eff;
+        const int cbytes = PAIR ? 32 : 16;
+        mbar_arrive_expect_tx(bar, (uint32_t) blocks * (uint32_t) (p.planes * p.plane_tx + p.b_bytes));
+        for (int gi = 0; gi < blocks; gi++) {
+          const int cg = (PAIR ? (it.cb * p.G) >> 1 : it.cb * p.G) + gi;
           const uint32_t dst = dst0 + (uint32_t) gi * p.cg_bytes;
           if constexpr (S == 1) {
-            tma_load_4d(dst, &tmap, cg * 16, it.ox0 + p.x_org[0], y0, it.n0, bar);
+            tma_load_4d(dst, &tmap, cg * cbytes, it.ox0 + p.x_org[0], y0, it.n0, bar);
           } else {
-            tma_load_5d(dst, &tmap, cg * 16, 0, it.ox0 + p.x_org[0], y0, it.n0, bar);
-            tma_load_5d(dst + p.plane_bytes, &tmap, cg * 16, 1, it.ox0 + p.x_org[1], y0, it.n0, bar);
+            tma_load_5d(dst, &tmap, cg * cbytes, 0, it.ox0 + p.x_org[0], y0, it.n0, bar);
+            tma_load_5d(dst + p.plane_bytes, &tmap, cg * cbytes, 1, it.ox0 + p.x_org[1], y0, it.n0, bar);
           }
           bulk_g2s(dst + p.a_bytes, p.wpack + (size_t) cg * p.b_bytes, (uint32_t) p.b_bytes, bar);
         }
@@ -393,7 +457,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     // concurrently (1 -> 4 warps: 2x faster; 4 -> 7: another 2-5 %); warp w owns the units w, w+7, ... of every item.
     // (ONE copy of the loop for all of them: per-warp template instances multiply the code and were measured 2.3x slower,
     // presumably instruction-cache misses)
-    mma_role<NB>(p, ctl, descs, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
+    if constexpr (PAIR) {
+      mma_role_pair(p, ctl, descs, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
+    } else {
+      mma_role<NB>(p, ctl, descs, smem_base, tmem_base, warp - kMmaWarp, first, step, total);
+    }
   } else {
     // ===================================== epilogue (16 warps) =====================================
     // Address and border-class arithmetic is split by how often it changes (the round-1 loop redid 64-bit pixel
@@ -452,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           valid = row_ok && ox < p.out_w;
         }
       };
-      if (p.store32) {
+      if (PAIR || p.store32) {
         // Channel groups in PAIRS: the lane requantises groups 2k and 2k+1 of its pixel back to back and writes their
         // 32 bytes with one 256-bit store = one full 32-byte sector per request.  (Per-group 16-byte stores are half-sector
         // writes: twice the requests on the L2, which this kernel loads to 55-75 % of its peak; without any stores it ran
@@ -469,12 +537,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           sub_tile(j);
           const int gi = 2 * gp;
           const bool two = gi + 1 < it.g_eff, lastp = pu + 4 >= pairs;
-          const uint4 lo = epilogue_unit<RQ, NB>(p, tbase + (uint32_t) (gi * p.mt + j) * NB, p.bias_cls + (bias_idx + (uint32_t) gi * 16u),
-                                                 lastp && !two, empty_bar);
+          // accumulator columns of (sub-tile j, group gi): pair mode keeps a pair's two groups side by side
+          const uint32_t tlo = tbase + (PAIR ? (uint32_t) (gp * p.mt + j) * 32u : (uint32_t) (gi * p.mt + j) * NB);
+          const uint32_t thi = PAIR ? tlo + 16u : tbase + (uint32_t) ((gi + 1) * p.mt + j) * NB;
+          const uint4 lo = epilogue_unit<RQ, NB>(p, tlo, p.bias_cls + (bias_idx + (uint32_t) gi * 16u), lastp && !two, empty_bar);
           uint8_t* const dst = obase + (dst_off + (uint32_t) gi * 16u);
           if (two) {
-            const uint4 hi = epilogue_unit<RQ, NB>(p, tbase + (uint32_t) ((gi + 1) * p.mt + j) * NB,
-                                                   p.bias_cls + (bias_idx + (uint32_t) (gi + 1) * 16u), lastp, empty_bar);
+            const uint4 hi = epilogue_unit<RQ, NB>(p, thi, p.bias_cls + (bias_idx + (uint32_t) (gi + 1) * 16u), lastp, empty_bar);
             if (valid) {
               // (pixel strides that are odd multiples of 16 bytes — C = 144 — leave every other pixel 16-byte aligned only:
               // those lanes write their two halves separately, 1.5 instead of 2 requests per 32 bytes on average)
@@ -525,9 +594,9 @@ static cudaError_t set_max_dynamic_smem(const void* kern, int max_smem_optin) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin - (int) fa.sharedSizeBytes);
 }
 
-template <int S, int RQ, int NB>
+template <int S, int RQ, int NB, bool PAIR = false>
 cudaError_t launch_one(const DwTcParams& p, const CUtensorMap& tm, int grid, int max_smem_optin, cudaStream_t stream) {
-  auto kern = q8_dwconv3x3_umma_kernel<S, RQ, NB>;
+  auto kern = q8_dwconv3x3_umma_kernel<S, RQ, NB, PAIR>;
   // once per instantiation, to the device maximum (a per-launch value raced between host threads; see the igemm launcher)
   static cudaError_t attr_status = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), max_smem_optin);
   if (attr_status != cudaSuccess) return attr_status;
@@ -537,6 +606,15 @@ cudaError_t launch_one(const DwTcParams& p, const CUtensorMap& tm, int grid, int
 
 template <int S, int NB>
 cudaError_t launch_rq(const DwTcParams& p, const CUtensorMap& tm, int grid, int max_smem_optin, cudaStream_t stream) {
+  if constexpr (NB == 16) {
+    if (p.pair) {
+      switch (p.rq_mode) {
+        case 5: return launch_one<S, 5, 16, true>(p, tm, grid, max_smem_optin, stream);
+        case 6: return launch_one<S, 6, 16, true>(p, tm, grid, max_smem_optin, stream);
+        default: return launch_one<S, 3, 16, true>(p, tm, grid, max_smem_optin, stream);
+      }
+    }
+  }
   switch (p.rq_mode) {
     case 5: return launch_one<S, 5, NB>(p, tm, grid, max_smem_optin, stream);
     case 6: return launch_one<S, 6, NB>(p, tm, grid, max_smem_optin, stream);

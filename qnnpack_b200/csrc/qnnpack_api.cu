@@ -182,36 +182,41 @@ constexpr int kCtlReserve = 2048;  // static SmemCtl + 1024-byte alignment slack
 
 // NHWC activations for the depthwise tensor-core kernel: stride 1 -> {C, W, H, N}; stride 2 -> {C, 2, W/2, H, N}
 // (even/odd input columns become a dimension of their own, so each parity plane is one dense box).
+// pair != 0: boxes of 32 channels (one full 32-byte sector per pixel and request) written with the 32-byte swizzle
 bool make_tmap_dw(CUtensorMap* tm, const uint8_t* in, size_t N, size_t H, size_t W, size_t C, size_t in_stride, int s,
-                  int box_px, int box_rows, int nb) {
+                  int box_px, int box_rows, int nb, int pair) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return false;
   const cuuint32_t estride[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t cb = pair ? 32 : 16;
+  const CUtensorMapSwizzle sw = pair ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   if (s == 1) {
     const cuuint64_t gdim[4] = {C, W, H, N};
     const cuuint64_t gstride[3] = {in_stride, W * in_stride, H * W * in_stride};
-    const cuuint32_t box[4] = {16, (cuuint32_t) box_px, (cuuint32_t) box_rows, (cuuint32_t) nb};
+    const cuuint32_t box[4] = {cb, (cuuint32_t) box_px, (cuuint32_t) box_rows, (cuuint32_t) nb};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   const cuuint64_t gdim[5] = {C, 2, W / 2, H, N};
   const cuuint64_t gstride[4] = {in_stride, 2 * in_stride, W * in_stride, H * W * in_stride};
-  const cuuint32_t box[5] = {16, 1, (cuuint32_t) box_px, (cuuint32_t) box_rows, (cuuint32_t) nb};
+  const cuuint32_t box[5] = {cb, 1, (cuuint32_t) box_px, (cuuint32_t) box_rows, (cuuint32_t) nb};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline int idiv_floor(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // Tiling of the depthwise tensor-core kernel (q8_dwconv_umma_sm100.cu).  Pure function of the geometry, so that the
 // CPU test can replay the smem addressing it prescribes.  Returns false when the shape is not eligible.
+// pair != 0 plans the channel-pair form (see DwTcParams::pair); it needs a single weight operand (wmode != 2).
 bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad_top, int pad_left, int wmode, int smem_optin,
-                  q8::DwTcParams* p) {
+                  q8::DwTcParams* p, int pair = 0) {
   if (C <= 0 || (C % 16) != 0 || (s != 1 && s != 2) || (s == 2 && (W % 2) != 0) || pad_top > 2 || pad_left > 2) return false;
   if (batch <= 0 || OH <= 0 || OW <= 0) return false;
+  if (pair && (wmode == 2 || C < 32)) return false;
   memset(p, 0, sizeof(*p));
+  p->pair = pair ? 1 : 0;
+  const int PB = pair ? 32 : 16;  // bytes of a pixel in a shared-memory plane
   p->batch = batch, p->channels = C, p->cgs = C / 16;
   p->in_h = H, p->in_w = W, p->out_h = OH, p->out_w = OW, p->stride = s, p->pad_top = pad_top, p->pad_left = pad_left;
   p->nb_cols = wmode == 2 ? 32 : 16;
@@ -258,7 +263,7 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   const int nsub = (OW + 7) / 8;
   const int umax = 256 / p->nb_cols;  // 8 (split operands) or 16 units
   const int smem_max = smem_optin - kCtlReserve - 1024;
-  p->b_bytes = q8::kDwTcTaps * 2 * p->nb_cols * 16;
+  p->b_bytes = pair ? q8::kDwTcTaps32 * 2 * 32 * 16 : q8::kDwTcTaps * 2 * p->nb_cols * 16;
   // QNNP_CUDA_DW_MT / QNNP_CUDA_DW_G: A/B overrides of the tile search (measurement only)
   const int env_mt = getenv("QNNP_CUDA_DW_MT") != nullptr ? atoi(getenv("QNNP_CUDA_DW_MT")) : 0;
   const int env_g = getenv("QNNP_CUDA_DW_G") != nullptr ? atoi(getenv("QNNP_CUDA_DW_G")) : 0;
@@ -274,16 +279,19 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
     const int mt = (nsub + xt - 1) / xt;
     const int box_px = 8 * mt + xoff_max;
     if (box_px > 256 || p->box_rows > 256) continue;
-    const int plane_tx = p->nb * p->box_rows * box_px * 16;
-    const int plane_bytes = (int) round_up(plane_tx, 128);
+    const int plane_tx = p->nb * p->box_rows * box_px * PB;
+    // (pair mode: planes start on whole 256-byte swizzle atoms, so that the TMA's and the UMMA's pattern — both functions of
+    // the absolute shared-memory address — agree wherever the box is placed)
+    const int plane_bytes = (int) round_up(plane_tx, pair ? 256 : 128);
     const int a_bytes = p->planes * plane_bytes;
-    const int cg_bytes = (int) round_up(a_bytes + p->b_bytes, 128);
+    const int cg_bytes = (int) round_up(a_bytes + p->b_bytes, pair ? 256 : 128);
     int G = umax / mt;
     if (env_g >= 1 && env_g < G) G = env_g;
     if (G > q8::kDwTcMaxG) G = q8::kDwTcMaxG;
-    if (G > p->cgs) G = p->cgs;
-    for (; G >= 1; G = (G > 2 ? G - 1 : G - 1)) {
-      const int stage_bytes = G * cg_bytes;
+    if (G > p->cgs) G = p->cgs + (pair ? (p->cgs & 1) : 0);
+    if (pair) G &= ~1;  // whole channel pairs (an odd group count leaves the last pair half empty)
+    for (; G >= 1; G -= (pair ? 2 : 1)) {
+      const int stage_bytes = pair ? (G / 2) * cg_bytes : G * cg_bytes;
       int stages = smem_max / stage_bytes;
       if (stages > q8::kDwTcMaxStages) stages = q8::kDwTcMaxStages;
       if (stages < 3 && !(cap == 1 && G == 1 && stages >= 2)) continue;
@@ -298,8 +306,11 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   if (p->mt == 0) return false;
   p->cblocks = (p->cgs + p->G - 1) / p->G;
   p->smem_total = p->num_stages * p->stage_bytes + 1024;
-  p->sbo = s * p->box_px * 16;
+  p->sbo = s * p->box_px * PB;
   if ((p->sbo >> 4) > 0x3FFF) return false;
+  if (pair)
+    for (int ky = 0; ky < 3; ky++)
+      for (int kx = 0; kx < 3; kx++) p->a_off9[ky * 3 + kx] = par[kx] * p->plane_bytes + (ky * p->box_px + xoff[kx]) * 32;
   // UMMA u multiplies two taps (K = 2 x 16 channels): (u,0)+(u,2) for kernel rows u = 0..2, (0,1)+(1,1), (2,1)+nothing
   const int t0[q8::kDwTcTaps][2] = {{0, 0}, {1, 0}, {2, 0}, {0, 1}, {2, 1}};
   const int t1[q8::kDwTcTaps][2] = {{0, 2}, {1, 2}, {2, 2}, {1, 1}, {2, 1}};
@@ -393,6 +404,7 @@ struct qnnp_operator {
   uint32_t* d_dw_wb = nullptr;
   int dw_wmode = 0;    // streaming depthwise kernel: 0 one s8 operand, 1 u8 (kzp == 0), 2 two s8 operands
   int dwtc_wmode = 0;  // tensor-core depthwise kernel: dw_tc_wmode()
+  uint8_t* d_dwtc_w32 = nullptr;  // ... its channel-pair operands (pack_dw_umma32_host), when the single-operand form applies
   uint8_t* d_dwtc_w = nullptr;     // dw tensor-core kernel: block-diagonal B operands (null if channels % 16 != 0)
   int32_t* d_dwtc_bias = nullptr;  // dw tensor-core kernel: [64 border classes][channels]
 
@@ -437,6 +449,7 @@ void free_operator(qnnp_operator* op) {
   cudaFree(op->d_dw_wa);
   cudaFree(op->d_dw_wb);
   cudaFree(op->d_dwtc_w);
+  cudaFree(op->d_dwtc_w32);
   cudaFree(op->d_dwtc_bias);
   cudaFree(op->d_in);
   cudaFree(op->d_out);
@@ -798,6 +811,23 @@ void pack_dw_umma_host(size_t C, const uint8_t* kernel, const int32_t* bias, int
       }
 }
 
+// Pair-mode B operands: per channel pair (32 channels) and tap one K-major no-swizzle block [2 K-chunks][32 rows][16 B] =
+// diag(w_tap[c] - kzp) over the pair's 32 channels (rows = output channel, K = input channel; chunk = K / 16).  Channels
+// beyond C (odd group count) keep zero weights.  wmode as in dw_tc_wmode() (never 2 here).
+void pack_dw_umma32_host(size_t C, const uint8_t* kernel, int kzp, int wmode, std::vector<uint8_t>& wp) {
+  const size_t pairs = (C + 31) / 32;
+  wp.assign(pairs * q8::kDwTcTaps32 * 1024, 0);
+  for (size_t pr = 0; pr < pairs; pr++)
+    for (int t = 0; t < q8::kDwTcTaps32; t++)
+      for (int n = 0; n < 32; n++) {
+        const size_t c = pr * 32 + n;
+        if (c >= C) continue;
+        const int32_t w = kernel[c * 9 + t], d = w - kzp;
+        const int32_t v = wmode == 1 ? w : (wmode == 3 ? -d : d);
+        wp[(pr * q8::kDwTcTaps32 + t) * 1024 + (size_t) (n / 16) * 512 + (size_t) n * 16 + (n % 16)] = (uint8_t) v;
+      }
+}
+
 enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int32_t* bias) {
   const size_t C = op->groups;
   op->c_pad = (int) round_up(C, 4);
@@ -856,6 +886,12 @@ enum qnnp_status pack_dw3x3(qnnp_operator* op, const uint8_t* kernel, const int3
     if (e == cudaSuccess) e = cudaMalloc((void**) &op->d_dwtc_bias, bc.size() * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_w, wp.data(), wp.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_bias, bc.data(), bc.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && op->dwtc_wmode != 2 && C >= 32) {  // channel-pair operands (DwTcParams::pair)
+      std::vector<uint8_t> wp32;
+      pack_dw_umma32_host(C, kernel, op->kzp, op->dwtc_wmode, wp32);
+      e = cudaMalloc((void**) &op->d_dwtc_w32, wp32.size());
+      if (e == cudaSuccess) e = cudaMemcpy(op->d_dwtc_w32, wp32.data(), wp32.size(), cudaMemcpyHostToDevice);
+    }
   }
   return map_cuda(e, "uploading depthwise weights");
 }
@@ -1175,18 +1211,30 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       const bool s2_rows = op->stride_h == 2 && 2 * (op->out_h - 1) + 3 > 32 && !env_set("QNNP_CUDA_DW_S2_UMMA") &&
           (op->dwtc_wmode == 2 || env_set("QNNP_CUDA_DW_S2_STREAM"));
       q8::DwTcParams& tp = pl.tp;
-      const bool tc_ok = stream_ok && op->d_dwtc_w != nullptr && !env_set("QNNP_CUDA_DW_NO_UMMA") && (force_tc || !s2_rows) &&
-          ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0 &&
+      const bool tc_base = stream_ok && op->d_dwtc_w != nullptr && !env_set("QNNP_CUDA_DW_NO_UMMA") && (force_tc || !s2_rows) &&
+          ((uintptr_t) in % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->in_stride % 16) == 0 && (op->out_stride % 16) == 0;
+      // channel-pair form (32-byte granularity on the L2 for the loads as well) where it was measured to win: stride 2, which
+      // reads four input bytes per output byte and ran at 74 % of the L2's request rate in the 16-channel form (112x112x96:
+      // 1.76 -> 1.20 ms, 14x14x576: 0.194 -> 0.161).  At stride 1 its larger weight blocks (9 KB per channel pair and item
+      // instead of 5 KB) cancel the gain (-1 % ... +14 %).  QNNP_CUDA_DW_PAIR=1 / QNNP_CUDA_DW_NO_PAIR=1 force it on / off.
+      const bool want_pair = (op->stride_h == 2 || env_set("QNNP_CUDA_DW_PAIR")) && !env_set("QNNP_CUDA_DW_NO_PAIR");
+      bool tc_ok = tc_base && op->d_dwtc_w32 != nullptr && want_pair &&
           plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
-                       (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dwtc_wmode, g_lib.max_smem_optin, &tp) &&
+                       (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dwtc_wmode, g_lib.max_smem_optin, &tp, 1) &&
           make_tmap_dw(&pl.dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
-                       tp.box_rows, tp.nb);
+                       tp.box_rows, tp.nb, 1);
+      if (!tc_ok)
+        tc_ok = tc_base &&
+            plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
+                         (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dwtc_wmode, g_lib.max_smem_optin, &tp, 0) &&
+            make_tmap_dw(&pl.dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
+                         tp.box_rows, tp.nb, 0);
       if (tc_ok) {
-        tp.out = out, tp.wpack = op->d_dwtc_w, tp.bias_cls = op->d_dwtc_bias;
+        tp.out = out, tp.wpack = tp.pair ? op->d_dwtc_w32 : op->d_dwtc_w, tp.bias_cls = op->d_dwtc_bias;
         tp.out_stride = (long long) op->out_stride;
         tp.rq = op->rq, tp.rq_mode = op->rq_mode;
         tp.acc_sign = op->dwtc_wmode == 3 ? -1 : 1;
-        tp.store32 = (tp.G % 2) == 0 && !env_set("QNNP_CUDA_DW_STORE16");
+        tp.store32 = tp.pair || ((tp.G % 2) == 0 && !env_set("QNNP_CUDA_DW_STORE16"));
         long long grid = persistent_grid(tp.total_items);
         tp.chunk = (int) ((tp.total_items + grid - 1) / grid);         // contiguous run of items per CTA
         grid = (tp.total_items + tp.chunk - 1) / tp.chunk;             // (CTAs that would start beyond the end are not launched)
@@ -1734,6 +1782,32 @@ QNNP_EXPORT int qnnp_cuda_debug_plan_dwconv(int channels, int batch, int in_h, i
                      p.a_lbo[4], p.sbo, p.nb_cols, p.b_signed, p.acc_stride, p.cblocks, p.cgs, (int) p.total_items, 0, 0};
   for (int i = 0; i < 40; i++) out[i] = v[i];
   return 1;
+}
+/* Channel-pair plan of the depthwise tensor-core kernel (DwTcParams::pair).  out[0..37] as qnnp_cuda_debug_plan_dwconv,
+ * out[38] = 1, out[39..47] = a_off9[ky*3+kx]. */
+QNNP_EXPORT int qnnp_cuda_debug_plan_dwconv32(int channels, int batch, int in_h, int in_w, int out_h, int out_w, int stride,
+                                              int pad_top, int pad_left, int wmode, int out[48]) {
+  q8::DwTcParams p;
+  const int optin = g_lib.initialized ? g_lib.max_smem_optin : 232448;
+  if (!plan_dw_umma(channels, batch, in_h, in_w, out_h, out_w, stride, pad_top, pad_left, wmode, optin, &p, 1)) return 0;
+  const int v[48] = {p.G, p.mt, p.xt, p.yt, p.nt, p.nb, p.Q, p.whole, p.planes, p.box_rows, p.box_px, p.plane_tx, p.plane_bytes,
+                     p.a_bytes, p.b_bytes, p.cg_bytes, p.stage_bytes, p.num_stages, p.smem_total, p.x_org[0], p.x_org[1],
+                     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, p.sbo, p.nb_cols, p.b_signed, p.acc_stride, p.cblocks, p.cgs, (int) p.total_items,
+                     1, p.a_off9[0], p.a_off9[1], p.a_off9[2], p.a_off9[3], p.a_off9[4], p.a_off9[5], p.a_off9[6], p.a_off9[7],
+                     p.a_off9[8]};
+  for (int i = 0; i < 48; i++) out[i] = v[i];
+  return 1;
+}
+/* Channel-pair B operands (pack_dw_umma32_host): wpack must hold ceil(channels / 32) * 9 * 1024 bytes.  Returns the operand
+ * mode (dw_tc_wmode), or -1 when the pair form does not apply. */
+QNNP_EXPORT int qnnp_cuda_debug_pack_dwconv32(size_t channels, uint8_t kernel_zero_point, const uint8_t* kernel, uint8_t* wpack) {
+  if (channels < 32 || (channels % 16) != 0) return -1;
+  const int wmode = dw_tc_wmode(channels, kernel, kernel_zero_point);
+  if (wmode == 2) return -1;
+  std::vector<uint8_t> wp;
+  pack_dw_umma32_host(channels, kernel, kernel_zero_point, wmode, wp);
+  memcpy(wpack, wp.data(), wp.size());
+  return wmode;
 }
 /* Packed operands of the tensor-core kernel for a K x N fully-connected / 1x1 operator, built on the host (no GPU needed).
  * meta = {folded, nkc, n_tiles, n_tile, n_mma, blk_chunks, bias_steps, b_signed, has_b2, k_tail_pad, has_corr, 0...}.
