@@ -74,6 +74,8 @@ struct DwTcParams {
                             // on the L2, SWIZZLE_32B tiles, one K = 32 UMMA per tap with a 32x32 diagonal B, N = 32); cg_bytes,
                             // plane_* and sbo then describe 32-byte pixels and one block per channel pair
   int a_off9[9];            // pair mode: byte offset of tap (ky, kx) = index ky*3+kx inside a pair's A block
+  int b_resident;           // 1: ALL weight blocks of the layer sit in shared memory for the whole launch (at b_res_off from the
+  int b_res_off;            // ring's base) instead of travelling with every item's stage; cg_bytes then has no B part
   int store32;              // 1: the epilogue pairs channel groups and writes 32 bytes per pixel with one 256-bit store
                             // (needs 32-byte aligned output pixels and an even number of channel groups per item)
   int acc_sign;             // +1, or -1 when the B operand holds kzp - w (the accumulators are the negated sums)

@@ -53,6 +53,7 @@ struct __align__(8) Ctl {
   uint64_t empty[kDwTcMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t b_full;  // resident weight blocks have landed (DwTcParams::b_resident)
   uint32_t tmem_base;
 };
 
@@ -265,8 +266,11 @@ __device__ __forceinline__ void mma_role_pair(const DwTcParams& p, Ctl& ctl, con
 #pragma unroll
   for (int t = 0; t < kDwTcTaps32; t++) {
     alo[t] = (((smem_base + (uint32_t) p.a_off9[t]) >> 4) & 0x3FFFu) | (1u << 16);
-    blo[t] = (uint32_t) umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) t * 1024u, 512, 0);
+    // resident weights: the blocks of ALL channel pairs sit behind the ring, indexed by the global pair
+    blo[t] = (uint32_t) umma_desc_kmajor_noswizzle(smem_base + (uint32_t) (p.b_resident ? p.b_res_off : p.a_bytes) + (uint32_t) t * 1024u,
+                                                   512, 0);
   }
+  if (p.b_resident) mbar_wait_parked(ctl_u + (uint32_t) offsetof(Ctl, b_full), 0);
   int stage = 0, as = 0, dslot = 0;
   uint32_t phase = 0, as_phase = 0;
   for (uint32_t item = first; item < total; item += step) {
@@ -274,6 +278,7 @@ __device__ __forceinline__ void mma_role_pair(const DwTcParams& p, Ctl& ctl, con
     const int mt_eff = __shfl_sync(0xffffffffu, descs[dslot].mt_eff, 0);
     const int g_eff = __shfl_sync(0xffffffffu, descs[dslot].g_eff, 0);
     const uint32_t inv = __shfl_sync(0xffffffffu, descs[dslot].inv, 0);
+    const uint32_t pair0 = (uint32_t) __shfl_sync(0xffffffffu, descs[dslot].c0, 0) >> 5;  // first channel pair of the item
     if (++dslot == kDescSlots) dslot = 0;
     const int units = mt_eff * ((g_eff + 1) >> 1);  // (sub-tile, channel pair), sub-tile fastest
     const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
@@ -287,8 +292,9 @@ __device__ __forceinline__ void mma_role_pair(const DwTcParams& p, Ctl& ctl, con
         if (un >= units) break;
         int j, gp;
         unit_split(un, mt_eff, inv, j, gp);
-        const uint32_t b16 = st16 + (((uint32_t) gp * p.cg_bytes) >> 4);  // operand offsets in 16-byte units
-        const uint32_t a16 = b16 + (uint32_t) j * 16;                      // 8 pixels x 32 bytes per sub-tile
+        const uint32_t s16 = st16 + (((uint32_t) gp * p.cg_bytes) >> 4);   // operand offsets in 16-byte units
+        const uint32_t a16 = s16 + (uint32_t) j * 16;                      // 8 pixels x 32 bytes per sub-tile
+        const uint32_t b16 = p.b_resident ? ((pair0 + (uint32_t) gp) * (uint32_t) p.b_bytes) >> 4 : s16;
         const uint32_t dcol = acc0 + (uint32_t) (gp * p.mt + j) * 32;
 #pragma unroll
         for (int t = 0; t < kDwTcTaps32; t++)
@@ -323,8 +329,10 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const It
 #pragma unroll
   for (int u = 0; u < kDwTcTaps; u++) {
     alo[u] = (uint32_t) umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_off[u], (uint32_t) p.a_lbo[u], 0);
-    blo[u] = (uint32_t) umma_desc_kmajor_noswizzle(smem_base + (uint32_t) p.a_bytes + (uint32_t) u * (2 * NB * 16), NB * 16, 0);
+    blo[u] = (uint32_t) umma_desc_kmajor_noswizzle(smem_base + (uint32_t) (p.b_resident ? p.b_res_off : p.a_bytes) +
+                                                       (uint32_t) u * (2 * NB * 16), NB * 16, 0);
   }
+  if (p.b_resident) mbar_wait_parked(ctl_u + (uint32_t) offsetof(Ctl, b_full), 0);
   int stage = 0, as = 0, dslot = 0;
   uint32_t phase = 0, as_phase = 0;
   for (uint32_t item = first; item < total; item += step) {
@@ -336,6 +344,7 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const It
     const int mt_eff = __shfl_sync(0xffffffffu, descs[dslot].mt_eff, 0);
     const int units = __shfl_sync(0xffffffffu, descs[dslot].units, 0);
     const uint32_t inv = __shfl_sync(0xffffffffu, descs[dslot].inv, 0);
+    const uint32_t group0 = (uint32_t) __shfl_sync(0xffffffffu, descs[dslot].c0, 0) >> 4;  // first channel group of the item
     if (++dslot == kDescSlots) dslot = 0;
     // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
     uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
@@ -344,8 +353,9 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const It
     for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
       int j, gi;
       unit_split(w + i * kMmaWarps, mt_eff, inv, j, gi);
-      b16[i] = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
-      a16[i] = b16[i] + (uint32_t) j * 8;
+      const uint32_t s16 = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
+      a16[i] = s16 + (uint32_t) j * 8;
+      b16[i] = p.b_resident ? ((group0 + (uint32_t) gi) * (uint32_t) p.b_bytes) >> 4 : s16;
       dcol[i] = tmem_u + (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
     }
     mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
@@ -389,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(smem_u32(&ctl.tmem_full[s]), kMmaWarps);
       mbar_init(smem_u32(&ctl.tmem_empty[s]), kEpiWarps * 32);
     }
+    mbar_init(smem_u32(&ctl.b_full), 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc<kTmemCols>(smem_u32(&ctl.tmem_base));
@@ -410,6 +421,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0, dslot = 0;
       uint32_t phase = 0;
+      if (p.b_resident) {  // every weight block of the layer, once
+        const uint32_t nbytes = (uint32_t) ((PAIR ? (p.cgs + 1) >> 1 : p.cgs) * p.b_bytes);
+        const uint32_t bar = smem_u32(&ctl.b_full);
+        mbar_arrive_expect_tx(bar, nbytes);
+        for (uint32_t o = 0; o < nbytes; o += 16384u)
+          bulk_g2s(smem_base + (uint32_t) p.b_res_off + o, p.wpack + o, nbytes - o < 16384u ? nbytes - o : 16384u, bar);
+      }
       ItemPos pos = first_pos(p, first);
       for (uint32_t item = first; item < total; item += step, advance_pos(p, pos)) {
         const DwItem it = make_item(p, pos);
@@ -434,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         // 32-byte sector of the input is requested once instead of twice); channels beyond C are zero-filled by the TMA
         const int blocks = PAIR ? (it.g_eff + 1) >> 1 : it.g_eff;
         const int cbytes = PAIR ? 32 : 16;
-        mbar_arrive_expect_tx(bar, (uint32_t) blocks * (uint32_t) (p.planes * p.plane_tx + p.b_bytes));
+        mbar_arrive_expect_tx(bar, (uint32_t) blocks * (uint32_t) (p.planes * p.plane_tx + (p.b_resident ? 0 : p.b_bytes)));
         for (int gi = 0; gi < blocks; gi++) {
           const int cg = (PAIR ? (it.cb * p.G) >> 1 : it.cb * p.G) + gi;
           const uint32_t dst = dst0 + (uint32_t) gi * p.cg_bytes;
@@ -444,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_5d(dst, &tmap, cg * cbytes, 0, it.ox0 + p.x_org[0], y0, it.n0, bar);
             tma_load_5d(dst + p.plane_bytes, &tmap, cg * cbytes, 1, it.ox0 + p.x_org[1], y0, it.n0, bar);
           }
-          bulk_g2s(dst + p.a_bytes, p.wpack + (size_t) cg * p.b_bytes, (uint32_t) p.b_bytes, bar);
+          if (!p.b_resident) bulk_g2s(dst + p.a_bytes, p.wpack + (size_t) cg * p.b_bytes, (uint32_t) p.b_bytes, bar);
         }
         if (++stage == p.num_stages) stage = 0, phase ^= 1;
       }

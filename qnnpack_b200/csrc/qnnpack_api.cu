@@ -306,6 +306,28 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
   if (p->mt == 0) return false;
   p->cblocks = (p->cgs + p->G - 1) / p->G;
   p->smem_total = p->num_stages * p->stage_bytes + 1024;
+  {
+    // Resident weights: a channel block's B operands are the same for every spatial tile, yet they travelled with every
+    // item's stage — 15 % of the bytes the kernel pulls from the L2 on the large images, 35-50 % on the 14x14 and 7x7 ones.
+    // When the whole layer's blocks fit beside >= 3 ring stages they are loaded once per CTA instead.
+    // (QNNP_CUDA_DW_B_STREAM=1 keeps them in the stages.)
+    const int blocks_total = pair ? (p->cgs + 1) / 2 : p->cgs, blocks_item = pair ? p->G / 2 : p->G;
+    const long long total_b = (long long) blocks_total * p->b_bytes;
+    const int cg2 = p->a_bytes;  // (already a multiple of the plane alignment)
+    const int stage2 = blocks_item * cg2;
+    int stages2 = (int) ((smem_max - total_b) / (stage2 > 0 ? stage2 : 1));
+    if (stages2 > q8::kDwTcMaxStages) stages2 = q8::kDwTcMaxStages;
+    // Measured (batch 4096): a win wherever the blocks are >= 20 % of an item's bytes (14x14x384: 0.302 -> 0.272 ms) and in
+    // the pair form (112x112x96 stride 2: 1.204 -> 1.163); with small blocks beside large tiles it LOSES 6 % (112x112x32,
+    // 16-channel form: 0.909 -> 0.966), so it is not used there.
+    const bool worth = pair || 4 * p->b_bytes >= p->a_bytes;
+    if (total_b <= 112 * 1024 && stages2 >= 3 && worth && getenv("QNNP_CUDA_DW_B_STREAM") == nullptr) {
+      p->b_resident = 1;
+      p->cg_bytes = cg2, p->stage_bytes = stage2, p->num_stages = stages2;
+      p->b_res_off = (int) round_up((size_t) stages2 * stage2, 256);
+      p->smem_total = p->b_res_off + (int) total_b + 1024;
+    }
+  }
   p->sbo = s * p->box_px * PB;
   if ((p->sbo >> 4) > 0x3FFF) return false;
   if (pair)
@@ -1217,10 +1239,13 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       // reads four input bytes per output byte and ran at 74 % of the L2's request rate in the 16-channel form (112x112x96:
       // 1.76 -> 1.20 ms, 14x14x576: 0.194 -> 0.161).  At stride 1 its larger weight blocks (9 KB per channel pair and item
       // instead of 5 KB) cancel the gain (-1 % ... +14 %).  QNNP_CUDA_DW_PAIR=1 / QNNP_CUDA_DW_NO_PAIR=1 force it on / off.
-      const bool want_pair = (op->stride_h == 2 || env_set("QNNP_CUDA_DW_PAIR")) && !env_set("QNNP_CUDA_DW_NO_PAIR");
-      bool tc_ok = tc_base && op->d_dwtc_w32 != nullptr && want_pair &&
+      // ... and at stride 1 where all of the layer's (larger) pair blocks can stay resident and the layer has >= 4 channel
+      // groups: 28x28x192 0.509 -> 0.460, 56x56x144 1.668 -> 1.629; not 112x112x32 (0.909 in the 16-channel form vs 0.946).
+      const bool pair_allowed = !env_set("QNNP_CUDA_DW_NO_PAIR") && tc_base && op->d_dwtc_w32 != nullptr;
+      bool tc_ok = pair_allowed &&
           plan_dw_umma((int) op->groups, (int) op->batch, (int) op->in_h, (int) op->in_w, (int) op->out_h, (int) op->out_w,
                        (int) op->stride_h, (int) op->pad_top, (int) op->pad_left, op->dwtc_wmode, g_lib.max_smem_optin, &tp, 1) &&
+          (op->stride_h == 2 || env_set("QNNP_CUDA_DW_PAIR") || (tp.b_resident && tp.cgs >= 4)) &&
           make_tmap_dw(&pl.dw_tmap, in, op->batch, op->in_h, op->in_w, op->groups, op->in_stride, (int) op->stride_h, tp.box_px,
                        tp.box_rows, tp.nb, 1);
       if (!tc_ok)

@@ -280,6 +280,118 @@ def test_kernel_replay_on_the_packed_operands(plan, c, n, h, w, s, pad, kzp, izp
     assert np.array_equal(bias_u.view(np.uint32), bias_cls.view(np.uint32) ^ np.uint32(0x80000000))
 
 
+NAMES32 = NAMES + ["pair"] + ["a_off9_%d" % t for t in range(9)]
+
+
+def replay_packed_pair(d, x, wpack32, bias_cls, signed_b, s, pad, oh, ow, acc_sign):
+    """Channel-pair form of the kernel (DwTcParams::pair), replayed on the library's own plan and packed operands.
+    Shared memory is modelled byte for byte: the TMA writes a box of 32-byte pixels with the 32-byte swizzle (16-byte chunk
+    index XOR bit 7 of the byte's shared-memory address; planes start on 256-byte boundaries), every UMMA row m reads the
+    32 bytes of the pixel its SWIZZLE_32B descriptor addresses — start = tap offset + sub-tile, 32 bytes per row, SBO per
+    8-row group — through the same XOR, and multiplies them with the tap's [2 K-chunks][32 rows][16 B] block."""
+    n, h, w, c = x.shape
+    assert d["pair"] == 1 and d["nb_cols"] == 16 and d["G"] % 2 == 0
+    acc = np.zeros((n, oh, ow, c), dtype=np.int64)
+    written = np.zeros((n, oh, ow, c), dtype=np.int32)
+    pairs_per_item = d["G"] // 2
+
+    def sw(addr):  # physical address of logical byte `addr` of a swizzled plane region
+        return addr ^ (((addr >> 7) & 1) << 4)
+
+    for item in range(d["total_items"]):
+        r, cb = divmod(item, d["cblocks"])
+        q, xtile = divmod(r, d["xt"])
+        nblk, ytile = divmod(q, d["yt"])
+        n0, oy0, ox0 = nblk * d["nb"], ytile * 16, xtile * d["mt"] * 8
+        mt_eff = min(d["mt"], (ow - ox0 + 7) // 8)
+        g_eff = min(d["G"], d["cgs"] - cb * d["G"])
+        y0 = (0 if d["whole"] else oy0 * s) - pad[0]
+        for gp in range((g_eff + 1) // 2):
+            pr = cb * pairs_per_item + gp                       # global channel pair
+            smem = np.zeros(d["a_bytes"] + 64 * 1024, dtype=np.uint8)
+            for par in range(d["planes"]):
+                xo = ox0 + (d["x_org0"], d["x_org1"])[par]
+                base = par * d["plane_bytes"]
+                assert base % 256 == 0
+                for i in range(d["nb"]):
+                    for ry in range(d["box_rows"]):
+                        for rx in range(d["box_px"]):
+                            iy = y0 + ry
+                            ix = (xo + rx) if s == 1 else 2 * (xo + rx) + par
+                            inb = (xo + rx) >= 0 and ((xo + rx) < w if s == 1 else (xo + rx) < w // 2)
+                            px = np.zeros(32, dtype=np.uint8)
+                            if n0 + i < n and 0 <= iy < h and inb and 0 <= ix < w:
+                                ch = x[n0 + i, iy, ix, pr * 32:pr * 32 + 32]    # channels beyond C: zero fill
+                                px[:len(ch)] = ch
+                            row = base + ((i * d["box_rows"] + ry) * d["box_px"] + rx) * 32
+                            for k in range(32):
+                                smem[sw(row + k)] = px[k]
+            for j in range(mt_eff):
+                a = np.zeros((128, 32), dtype=np.int64)
+                for t in range(9):
+                    blk = wpack32[(pr * 9 + t) * 1024:(pr * 9 + t + 1) * 1024].reshape(2, 32, 16)
+                    bmat = (blk.view(np.int8) if signed_b else blk).astype(np.int64)       # [chunk][n][k % 16]
+                    bfull = np.concatenate([bmat[0], bmat[1]], axis=1)                      # [n][k]
+                    start = d["a_off9_%d" % t] + j * 256
+                    rows = np.zeros((128, 32), dtype=np.int64)
+                    for m in range(128):
+                        ra = start + (m // 8) * d["sbo"] + (m % 8) * 32
+                        rows[m] = [smem[sw(ra + k)] for k in range(32)]
+                    a += rows @ bfull.T
+                for m in range(128):
+                    g, px_ = divmod(m, 8)
+                    img, oyl = divmod(g, d["Q"])
+                    nn, oy, ox = n0 + img, oy0 + oyl, ox0 + 8 * j + px_
+                    if not (img < d["nb"] and nn < n and oy < oh and ox < ow):
+                        continue
+                    iy0, ix0 = oy * s - pad[0], ox * s - pad[1]
+                    rm = sum(1 << ky for ky in range(3) if 0 <= iy0 + ky < h)
+                    cm = sum(1 << kx for kx in range(3) if 0 <= ix0 + kx < w)
+                    for half in range(2):
+                        gi = 2 * gp + half
+                        if gi >= g_eff:
+                            continue
+                        c0 = (cb * d["G"] + gi) * 16
+                        acc[nn, oy, ox, c0:c0 + 16] = acc_sign * a[m, 16 * half:16 * half + 16] + bias_cls[rm * 8 + cm, c0:c0 + 16]
+                        written[nn, oy, ox, c0:c0 + 16] += 1
+    assert (written == 1).all()
+    return acc
+
+
+@pytest.mark.parametrize("kzp,izp", [(127, 131), (128, 7), (0, 255)])
+@pytest.mark.parametrize("c,n,h,w,s,pad", [(32, 2, 12, 13, 1, (1, 1)), (96, 1, 20, 22, 2, (1, 1)), (48, 3, 7, 7, 1, (1, 1)),
+                                            (32, 1, 22, 10, 2, (0, 1)), (144, 1, 9, 9, 1, (1, 1))])
+def test_pair_form_replay_on_the_packed_operands(c, n, h, w, s, pad, kzp, izp):
+    """The channel-pair form (32-byte pixels, SWIZZLE_32B tiles, one K = 32 UMMA per tap): the library's plan and packed
+    operands reproduce the reference accumulators, every output exactly once — odd group counts (C = 48, 144) included."""
+    from qnnpack_b200 import build
+    lib = C.CDLL(build.build())
+    lib.qnnp_cuda_debug_plan_dwconv32.argtypes = [C.c_int] * 10 + [C.POINTER(C.c_int)]
+    lib.qnnp_cuda_debug_pack_dwconv32.argtypes = [C.c_size_t, C.c_uint8, C.c_void_p, C.c_void_p]
+    lib.qnnp_cuda_debug_pack_dwconv.argtypes = [C.c_size_t, C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_void_p]
+    rng = np.random.default_rng(c * 3 + h + kzp)
+    wk = rng.integers(0, 256, (c, 9), dtype=np.uint8)
+    if kzp == 127:
+        wk[0, 0], wk[-1, 8] = 0, 255
+    bias = rng.integers(-50000, 50000, c).astype(np.int32)
+    wpack32 = np.zeros(((c + 31) // 32) * 9 * 1024, dtype=np.uint8)
+    wmode = lib.qnnp_cuda_debug_pack_dwconv32(c, kzp, wk.ctypes.data, wpack32.ctypes.data)
+    assert wmode == {127: 3, 128: 0, 0: 1}[kzp]
+    bias_cls = np.zeros((64, c), dtype=np.int32)
+    wpack16 = np.zeros((c // 16) * 5 * 2 * 32 * 16, dtype=np.uint8)
+    assert lib.qnnp_cuda_debug_pack_dwconv(c, izp, kzp, wk.ctypes.data, bias.ctypes.data, 0, wpack16.ctypes.data,
+                                           bias_cls.ctypes.data) == wmode
+    oh, ow = (h + 2 * pad[0] - 3) // s + 1, (w + 2 * pad[1] - 3) // s + 1
+    out = (C.c_int * 48)()
+    assert lib.qnnp_cuda_debug_plan_dwconv32(c, n, h, w, oh, ow, s, pad[0], pad[1], wmode, out)
+    d = dict(zip(NAMES32, out))
+    assert d["smem_total"] <= SMEM_OPTIN and d["stage_bytes"] == (d["G"] // 2) * d["cg_bytes"] and d["cg_bytes"] % 256 == 0
+    x = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+    got = replay_packed_pair(d, x, wpack32, bias_cls.astype(np.int64), wmode != 1, s, pad, oh, ow, -1 if wmode == 3 else 1)
+    assert np.array_equal(got, direct(x, wk, bias.astype(np.int64), izp, kzp, s, pad, oh, ow))
+
+
 def test_item_stepping_is_equivalent_to_decoding():
     """Model of the kernel's item walk (q8_dwconv_umma_sm100.cu: first_pos / advance_pos with the host's step digits):
     a CTA's k-th item, reached by adding the grid size in (cb, xtile, ytile, nblk) digits with carries, must be the item
