@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_arrive_expect_tx(bar, (uint32_t) (it.mt_eff * p.skc) * kChunkBytes + b_bytes);
             for (int j = 0; j < it.mt_eff; j++)
               tma_load_3d(a_stage + (uint32_t) (j * p.skc) * kChunkBytes, &tmap_a, 0, (int) (it.m0 + (long long) j * kTileM),
-                          ks * p.skc, bar);
+                          p.a_sw32 ? (ks * p.skc) >> 1 : ks * p.skc, bar);
             if (!p.b_resident) {
               const uint8_t* wsrc =
                   p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.blk_chunks + (size_t) ks * p.skc) * p.n_mma * 16;
@@ -941,6 +941,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       // descriptor templates (strides, version); the 16-byte-granular start address is added per use — every operand
       // lies below 256 KB, so the 14-bit address field cannot carry into its neighbours
       const uint64_t a_tmpl = umma_desc_kmajor_noswizzle(0, kChunkBytes, 128);
+      // activations: 16-byte chunks (no swizzle: two chunks = one K = 32 step, LBO apart) or 32-byte slabs written by the TMA
+      // with the 32-byte swizzle (one slab = one K step; layout type 6, 8-row groups 256 bytes apart).  Slab s sits where
+      // chunks 2s, 2s+1 sat, so the per-step byte offsets below are the same for both.
+      const uint64_t a_main = p.a_sw32 ? (((uint64_t) 1 << 16) | ((uint64_t) (256u >> 4) << 32) | ((uint64_t) 1 << 46) | ((uint64_t) 6 << 61))
+                                       : a_tmpl;
       const uint64_t b_tmpl = umma_desc_kmajor_noswizzle(0, b_lbo, 128);
       if (p.b_resident) {
         mbar_wait(ctl_u + (uint32_t) offsetof(SmemCtl, b_full), 0);
@@ -981,7 +986,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int c = 0; c < cs; c += 2) {
               const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
               const uint64_t bd = b_tmpl + ((b_base + c * b_lbo) >> 4);
-              const uint64_t ad0 = a_tmpl + ((a_stage + c * kChunkBytes) >> 4);
+              const uint64_t ad0 = a_main + ((a_stage + c * kChunkBytes) >> 4);
               const uint32_t sub16 = sub_bytes >> 4;
               for (int j = w; j < it.mt_eff; j += kMmaWarps)
                 umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, bd, idesc_main, acc);

@@ -63,6 +63,7 @@ struct IgemmParams {
 
   // smem carve-up (byte offsets into dynamic smem, 1024-aligned base)
   int smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, staging_bytes, smem_total;
+  int a_sw32;          // TMA loader: activations arrive as 32-byte K slabs in SWIZZLE_32B tiles (K % 32 == 0) instead of 16-byte chunks
   int staging_bufs;    // output staging buffers per epilogue pair: 1, or 2 used alternately (panel epilogue, when smem allows)
   int smem_raw_off, raw_cap, raw_bufs;  // raw-row staging (3x3x3 stem loader): raw_bufs (2..4) buffers of raw_cap bytes
   int raw_batch;              // images in the input tensor (bounds the bulk copies)

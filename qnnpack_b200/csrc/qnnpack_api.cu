@@ -134,9 +134,21 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // Activation matrix [M][in_stride] (first K bytes of a row used) as {16 B of K, M rows, K/16 chunks}; box = {16, 128, skc}.
-bool make_tmap_a(CUtensorMap* tm, const uint8_t* in, size_t M, size_t in_stride, int K, int skc) {
+// sw32 != 0 (K % 32 == 0): 32-byte K slabs instead of 16-byte chunks — {32 B, M rows, K/32 slabs}, box {32, 128, skc/2},
+// written with the 32-byte swizzle.  Same bytes at the same shared-memory offsets per (slab, row) block, but every 32-byte
+// sector of the activations is requested from the L2 once instead of twice.
+bool make_tmap_a(CUtensorMap* tm, const uint8_t* in, size_t M, size_t in_stride, int K, int skc, int sw32) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return false;
+  if (sw32) {
+    const cuuint64_t gdim[3] = {32, (cuuint64_t) M, (cuuint64_t) (K / 32)};
+    const cuuint64_t gstride[2] = {(cuuint64_t) in_stride, 32};
+    const cuuint32_t box[3] = {32, (cuuint32_t) q8::kTileM, (cuuint32_t) (skc / 2)};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(in), gdim, gstride, box, estride,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   const cuuint64_t gdim[3] = {16, (cuuint64_t) M, (cuuint64_t) (K / 16)};
   const cuuint64_t gstride[2] = {(cuuint64_t) in_stride, 16};
   const cuuint32_t box[3] = {16, (cuuint32_t) q8::kTileM, (cuuint32_t) skc};
@@ -1152,10 +1164,12 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       }
       // 1x1 / FC with 16-byte aligned rows: the TMA loads the activation tiles
       pl.has_tmap_a = false;
+      const int a_sw32 = ((op->K % 32) == 0 && (op->skc % 2) == 0 && !env_set("QNNP_CUDA_NO_A_SW32")) ? 1 : 0;
       if (mode == q8::kModeGemm && vec == 16 && op->groups == 1 && (op->K % 16) == 0 && op->skc <= 256 && M < (1ull << 31) &&
-          !env_set("QNNP_CUDA_NO_TMA") && make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K, op->skc)) {
+          !env_set("QNNP_CUDA_NO_TMA") && make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K, op->skc, a_sw32)) {
         vec = 32;
         pl.has_tmap_a = true;
+        p.a_sw32 = a_sw32;
       }
       // panel epilogue: a second staging buffer per epilogue pair when shared memory allows — the shallow-K layers (where the
       // epilogue is the long pole) have far more ring stages than they can use, so stages beyond "3 items of K or 64 KB in
