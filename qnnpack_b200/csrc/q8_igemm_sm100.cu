@@ -872,9 +872,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             cs = cs < p.skc ? cs : p.skc;
             const uint32_t b_bytes = p.b_resident ? 0u : (uint32_t) (cs * p.n_mma) * 16u;
             mbar_arrive_expect_tx(bar, (uint32_t) (it.mt_eff * p.skc) * kChunkBytes + b_bytes);
-            for (int j = 0; j < it.mt_eff; j++)
-              tma_load_3d(a_stage + (uint32_t) (j * p.skc) * kChunkBytes, &tmap_a, 0, (int) (it.m0 + (long long) j * kTileM),
-                          p.a_sw32 ? (ks * p.skc) >> 1 : ks * p.skc, bar);
+            for (int j = 0; j < it.mt_eff; j++) {
+              const uint32_t dst = a_stage + (uint32_t) (j * p.skc) * kChunkBytes;
+              const int row0 = (int) (it.m0 + (long long) j * kTileM);
+              tma_load_3d(dst, &tmap_a, 0, row0, p.a_sw32 ? (ks * p.skc) >> 1 : ks * p.skc, bar);
+              if (p.a_sw32 == 2)  // K % 32 == 16: the last 16 bytes of K (+ a zero-filled partner chunk) behind the slabs
+                tma_load_3d(dst + (uint32_t) p.a_tail_c * kChunkBytes, reinterpret_cast<const CUtensorMap*>(&smaps.m[4][0]), 0, row0,
+                            p.a_tail_c, bar);
+            }
             if (!p.b_resident) {
               const uint8_t* wsrc =
                   p.wpack + ((size_t) (it.g * p.n_tiles + it.nt) * p.blk_chunks + (size_t) ks * p.skc) * p.n_mma * 16;
@@ -986,7 +991,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int c = 0; c < cs; c += 2) {
               const uint32_t acc = (p.folded || (ks | c) != 0) ? 1u : 0u;
               const uint64_t bd = b_tmpl + ((b_base + c * b_lbo) >> 4);
-              const uint64_t ad0 = a_main + ((a_stage + c * kChunkBytes) >> 4);
+              const uint64_t ad0 = ((p.a_sw32 == 2 && c >= p.a_tail_c) ? a_tmpl : a_main) + ((a_stage + c * kChunkBytes) >> 4);
               const uint32_t sub16 = sub_bytes >> 4;
               for (int j = w; j < it.mt_eff; j += kMmaWarps)
                 umma_i8(d_tmem + j * p.n_mma, ad0 + (uint32_t) j * sub16, bd, idesc_main, acc);

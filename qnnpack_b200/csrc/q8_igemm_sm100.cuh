@@ -63,7 +63,10 @@ struct IgemmParams {
 
   // smem carve-up (byte offsets into dynamic smem, 1024-aligned base)
   int smem_b_off, smem_bias_off, smem_a_off, smem_stage_off, staging_bytes, smem_total;
-  int a_sw32;          // TMA loader: activations arrive as 32-byte K slabs in SWIZZLE_32B tiles (K % 32 == 0) instead of 16-byte chunks
+  int a_sw32;          // TMA loader: 1 = activations arrive as 32-byte K slabs in SWIZZLE_32B tiles (K % 32 == 0) instead of 16-byte
+                       // chunks; 2 = K % 32 == 16 and one K stage: slabs for the first a_tail_c chunks, the last 16 bytes of K as a
+                       // chunk pair (second chunk zero-filled) through the no-swizzle view in IgemmStoreMaps::m[4]
+  int a_tail_c;
   int staging_bufs;    // output staging buffers per epilogue pair: 1, or 2 used alternately (panel epilogue, when smem allows)
   int smem_raw_off, raw_cap, raw_bufs;  // raw-row staging (3x3x3 stem loader): raw_bufs (2..4) buffers of raw_cap bytes
   int raw_batch;              // images in the input tensor (bounds the bulk copies)
@@ -91,7 +94,8 @@ struct IgemmParams {
 
 // tensor maps of the output for the panel epilogue, one per panel-width class
 struct IgemmStoreMaps {
-  alignas(64) unsigned char m[4][128];
+  // [0..3]: output panels by width class; [4]: 16-byte-chunk view of the activations for the K tail (IgemmParams::a_sw32 == 2)
+  alignas(64) unsigned char m[5][128];
 };
 
 }  // namespace q8

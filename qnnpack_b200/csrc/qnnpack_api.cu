@@ -1164,12 +1164,23 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       }
       // 1x1 / FC with 16-byte aligned rows: the TMA loads the activation tiles
       pl.has_tmap_a = false;
-      const int a_sw32 = ((op->K % 32) == 0 && (op->skc % 2) == 0 && !env_set("QNNP_CUDA_NO_A_SW32")) ? 1 : 0;
+      // 32-byte slabs when K % 32 == 0; when K % 32 == 16 and the whole K is one stage (K = 144), slabs for the first
+      // K - 16 bytes plus the last chunk through the 16-byte view (its partner chunk is out of bounds: zero-filled)
+      int a_sw32 = 0;
+      if (!env_set("QNNP_CUDA_NO_A_SW32") && (op->skc % 2) == 0) {
+        if ((op->K % 32) == 0) a_sw32 = 1;
+        else if ((op->K % 32) == 16 && op->K > 32 && op->k_stages == 1 && op->skc * 16 == op->K + 16) a_sw32 = 2;
+      }
       if (mode == q8::kModeGemm && vec == 16 && op->groups == 1 && (op->K % 16) == 0 && op->skc <= 256 && M < (1ull << 31) &&
-          !env_set("QNNP_CUDA_NO_TMA") && make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K, op->skc, a_sw32)) {
+          !env_set("QNNP_CUDA_NO_TMA") &&
+          (a_sw32 == 2 ? make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K - 16, op->skc - 2, 1) &&
+                             make_tmap_a(reinterpret_cast<CUtensorMap*>(&pl.smaps.m[4][0]), in, M, op->in_stride, op->K, 2, 0)
+                       : make_tmap_a(&pl.tmap_a, in, M, op->in_stride, op->K, op->skc, a_sw32))) {
         vec = 32;
         pl.has_tmap_a = true;
         p.a_sw32 = a_sw32;
+        p.a_tail_c = op->skc - 2;
+        if (a_sw32 == 2) pl.has_smaps = true;  // (the tail view travels in the store-map block)
       }
       // panel epilogue: a second staging buffer per epilogue pair when shared memory allows — the shallow-K layers (where the
       // epilogue is the long pole) have far more ring stages than they can use, so stages beyond "3 items of K or 64 KB in
