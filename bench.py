@@ -34,11 +34,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at batch 4096, from the committed ncu --set full captures
-NCU_DRAM_BYTES_PER_LAUNCH = {"stem": 2.209e9, "b1_project": 2.438e9, "b2_expand": 5.704e9, "b1_dw": 3.278e9, "b2_dw": 6.187e9,
-                             "b3_dw": 3.917e9}
-NCU_DRAM_SOURCE = {"stem": "profiles/r2m_igemm_first3.summary.txt", "b1_project": "profiles/r2m_igemm_first3.summary.txt",
-                   "b2_expand": "profiles/r2m_igemm_first3.summary.txt", "b1_dw": "profiles/r2t_dw_umma_first3.summary.txt",
-                   "b2_dw": "profiles/r2t_dw_umma_first3.summary.txt", "b3_dw": "profiles/r2t_dw_umma_first3.summary.txt"}
+NCU_DRAM_BYTES_PER_LAUNCH = {"stem": 2.209e9, "b1_project": 2.435e9, "b2_expand": 5.705e9, "b1_dw": 3.239e9, "b2_dw": 6.170e9,
+                             "b3_dw": 3.791e9}
+NCU_DRAM_SOURCE = {"stem": "profiles/r2w_igemm_first3.summary.txt", "b1_project": "profiles/r2w_igemm_first3.summary.txt",
+                   "b2_expand": "profiles/r2w_igemm_first3.summary.txt", "b1_dw": "profiles/r2w_dw_umma_first3.summary.txt",
+                   "b2_dw": "profiles/r2w_dw_umma_first3.summary.txt", "b3_dw": "profiles/r2w_dw_umma_first3.summary.txt"}
 INT8_PEAK_TOPS_NOMINAL = 4500.0  # B200 dense int8 (task statement; not in MEASURED_PEAKS.json)
 
 
