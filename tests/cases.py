@@ -241,6 +241,15 @@ DW_TC_CASES = [
     conv_case("tc_c64_56_kzp1_two_operands", 2, 56, 56, 64, 1, 1, kzp=1, **DW_TC),
     conv_case("tc_c32_s2_rows_kzp128", 1, 40, 36, 32, 1, 1, stride=(2, 2), kzp=128, **DW_TC),
     conv_case("tc_c144_56_b2_negated", 2, 56, 56, 144, 1, 1, **DW_TC),
+    # channel-pair form (32-channel TMA boxes): odd group counts (last pair half empty), stride 2 with both parity planes,
+    # stacked whole images, many pairs per item
+    conv_case("tc_c48_s2_rows_odd_groups", 2, 40, 36, 48, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c144_s2_28_b3", 3, 28, 28, 144, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c96_s2_112", 1, 112, 112, 96, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c192_28_b3", 3, 28, 28, 192, 1, 1, **DW_TC),
+    conv_case("tc_c384_14_b5", 5, 14, 14, 384, 1, 1, **DW_TC),
+    conv_case("tc_c576_s2_14_b4", 4, 14, 14, 576, 1, 1, stride=(2, 2), **DW_TC),
+    conv_case("tc_c960_7_b6_streamed_weights", 6, 7, 7, 960, 1, 1, **DW_TC),
 ]
 
 STEM_CASES = [

@@ -58,6 +58,28 @@ def test_q8dwconv_tensor_core_path(gpu_lib, oracle_c, case, monkeypatch):
     U.assert_same_bytes(got, U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
 
 
+# every form of the tcgen05 depthwise kernel on the same shapes: channel-pair form forced on / off, weight blocks resident or
+# travelling with every item, 16-byte stores (the router's own choice is what test_q8dwconv_tensor_core_path runs)
+DW_FORMS = [dict(QNNP_CUDA_DW_PAIR="1"), dict(QNNP_CUDA_DW_NO_PAIR="1"), dict(QNNP_CUDA_DW_PAIR="1", QNNP_CUDA_DW_B_STREAM="1"),
+            dict(QNNP_CUDA_DW_NO_PAIR="1", QNNP_CUDA_DW_B_STREAM="1", QNNP_CUDA_DW_STORE16="1")]
+DW_FORM_CASES = [c for c in CS.DW_TC_CASES if c["name"] in (
+    "tc_c32_14x14", "tc_c32_s2_rows", "tc_c48_7x7_stack2", "tc_c160_112", "tc_c144_56_b2_negated", "tc_c48_s2_rows_odd_groups",
+    "tc_c144_s2_28_b3", "tc_c192_28_b3", "tc_c384_14_b5", "tc_c32_out_stride", "tc_c64_kzp0_u8", "tc_c64_kzp128_s8")]
+
+
+@pytest.mark.parametrize("form", DW_FORMS, ids=lambda f: "+".join(k[13:].lower() for k in f))
+@pytest.mark.parametrize("case", DW_FORM_CASES, ids=lambda c: c["name"])
+def test_q8dwconv_tensor_core_forms(gpu_lib, oracle_c, case, form, monkeypatch):
+    monkeypatch.setenv("QNNP_CUDA_DW_UMMA", "1")
+    for k, v in form.items():
+        monkeypatch.setenv(k, v)
+    x, k, b, kw = U.conv_setup(case)
+    before = gpu_lib.dw_umma_launch_count()
+    got = U.run_conv(gpu_lib, case, x, k, b, kw)
+    assert gpu_lib.dw_umma_launch_count() == before + 1, "expected the tcgen05 depthwise kernel"
+    U.assert_same_bytes(got, U.run_conv(oracle_c, case, x, k, b, kw), case["name"])
+
+
 # 3x3 over 3 dense channels (the MobileNetV2 stem shape class): run loader fed from bulk-staged raw rows; the items
 # of these cases straddle image boundaries and rows that are not multiples of 16 bytes
 
