@@ -333,7 +333,7 @@ bool plan_dw_umma(int C, int batch, int H, int W, int OH, int OW, int s, int pad
     // the pair form (112x112x96 stride 2: 1.204 -> 1.163); with small blocks beside large tiles it LOSES 6 % (112x112x32,
     // 16-channel form: 0.909 -> 0.966), so it is not used there.
     const bool worth = pair || 4 * p->b_bytes >= p->a_bytes;
-    if (total_b <= 112 * 1024 && stages2 >= 3 && worth && getenv("QNNP_CUDA_DW_B_STREAM") == nullptr) {
+    if (total_b <= 160 * 1024 && stages2 >= 3 && worth && getenv("QNNP_CUDA_DW_B_STREAM") == nullptr) {
       p->b_resident = 1;
       p->cg_bytes = cg2, p->stage_bytes = stage2, p->num_stages = stages2;
       p->b_res_off = (int) round_up((size_t) stages2 * stage2, 256);
