@@ -346,30 +346,27 @@ __device__ __forceinline__ void mma_role(const DwTcParams& p, Ctl& ctl, const It
     const uint32_t inv = __shfl_sync(0xffffffffu, descs[dslot].inv, 0);
     const uint32_t group0 = (uint32_t) __shfl_sync(0xffffffffu, descs[dslot].c0, 0) >> 4;  // first channel group of the item
     if (++dslot == kDescSlots) dslot = 0;
-    // per-unit operand offsets (16-byte units) and accumulator columns of this warp's units
-    uint32_t a16[kMaxUnitsPerMmaWarp], b16[kMaxUnitsPerMmaWarp], dcol[kMaxUnitsPerMmaWarp];
     const uint32_t st16 = ((uint32_t) stage * p.stage_bytes) >> 4;
-#pragma unroll
-    for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
-      int j, gi;
-      unit_split(w + i * kMmaWarps, mt_eff, inv, j, gi);
-      const uint32_t s16 = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);
-      a16[i] = s16 + (uint32_t) j * 8;
-      b16[i] = p.b_resident ? ((group0 + (uint32_t) gi) * (uint32_t) p.b_bytes) >> 4 : s16;
-      dcol[i] = tmem_u + (uint32_t) as * p.acc_stride + (uint32_t) (gi * p.mt + j) * NB;
-    }
+    const uint32_t acc0 = tmem_u + (uint32_t) as * p.acc_stride;
     mbar_wait_parked(bar_tempty + 8u * (uint32_t) as, as_phase ^ 1);
     tc_fence_after_sync();
     if (elect_one()) {
-      // the 5 UMMAs of a unit accumulate into the same columns and would serialise back to back: taps are the
-      // outer loop, so consecutive instructions hit different accumulators
+      // this warp's units w, w + 7, ...: a (uniform) early exit instead of predicated-off slots — the straight-line version
+      // executed the operand arithmetic of all 15 slots for every item.  The 5 UMMAs of a unit accumulate into the same
+      // columns; the other issuing warps' instructions interleave with them in the tensor pipe's queue.
 #pragma unroll
-      for (int u = 0; u < kDwTcTaps; u++) {
+      for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
+        const int un = w + i * kMmaWarps;
+        if (un >= units) break;
+        int j, gi;
+        unit_split(un, mt_eff, inv, j, gi);
+        const uint32_t s16 = st16 + (((uint32_t) gi * p.cg_bytes) >> 4);  // operand offsets in 16-byte units
+        const uint32_t a16 = s16 + (uint32_t) j * 8;
+        const uint32_t b16 = p.b_resident ? ((group0 + (uint32_t) gi) * (uint32_t) p.b_bytes) >> 4 : s16;
+        const uint32_t dcol = acc0 + (uint32_t) (gi * p.mt + j) * NB;
 #pragma unroll
-        for (int i = 0; i < kMaxUnitsPerMmaWarp; i++) {
-          if (w + i * kMmaWarps < units)
-            umma_i8(dcol[i], pack_u64(alo[u] + a16[i], ahi), pack_u64(blo[u] + b16[i], bhi), idesc, u > 0 ? 1u : 0u);
-        }
+        for (int u = 0; u < kDwTcTaps; u++)
+          umma_i8(dcol, pack_u64(alo[u] + a16, ahi), pack_u64(blo[u] + b16, bhi), idesc, u > 0 ? 1u : 0u);
       }
       umma_commit(bar_empty + 8u * (uint32_t) stage);  // smem stage may be refilled once these UMMAs have read it
       umma_commit(bar_tfull + 8u * (uint32_t) as);     // this warp's share of the accumulators is complete
@@ -529,13 +526,22 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto sub_tile = [&](int j) {  // column class, validity and byte offset of this lane's pixel in sub-tile j
         if (j != j_cur) {
           j_cur = j;
-          const int ox = it.ox0 + 8 * j + px;
-          const int ix0 = ox * S - p.pad_left;
-          const int clo = ix0 < 0 ? -ix0 : 0, chi = ix0 + 3 - p.in_w > 0 ? ix0 + 3 - p.in_w : 0;
-          const uint32_t cm = chi >= 3 ? 0u : (((7u << clo) & 7u) & (7u >> chi));
-          bias_idx = bias_row + cm * (uint32_t) p.channels;
           dst_off = lane_off + (uint32_t) j * sub_step;
-          valid = row_ok && ox < p.out_w;
+          // Sub-tiles that touch neither the left nor the right image border — all but two per image row — have all three
+          // tap columns inside the image for every lane: column class 7, every column valid.  The test is warp-uniform
+          // (item and sub-tile only); the general form costs ~25 instructions.
+          const int ox_first = it.ox0 + 8 * j;
+          if (ox_first * S - p.pad_left >= 0 && (ox_first + 7) * S - p.pad_left + 3 <= p.in_w) {
+            bias_idx = bias_row + 7u * (uint32_t) p.channels;
+            valid = row_ok;
+          } else {
+            const int ox = ox_first + px;
+            const int ix0 = ox * S - p.pad_left;
+            const int clo = ix0 < 0 ? -ix0 : 0, chi = ix0 + 3 - p.in_w > 0 ? ix0 + 3 - p.in_w : 0;
+            const uint32_t cm = chi >= 3 ? 0u : (((7u << clo) & 7u) & (7u >> chi));
+            bias_idx = bias_row + cm * (uint32_t) p.channels;
+            valid = row_ok && ox < p.out_w;
+          }
         }
       };
       if (PAIR || p.store32) {
