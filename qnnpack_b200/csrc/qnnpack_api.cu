@@ -1208,8 +1208,9 @@ enum qnnp_status build_plan(qnnp_operator* op, const uint8_t* in, const uint8_t*
       pl.path = kPlanIgemm;
       // large GEMMs (weights not resident): the CTA-pair kernel, when the operands can be described to the TMA
       // (8 epilogue warps per CTA: the pair kernel wins where the tensor pipe / weight streaming is the long pole, i.e. deep
-      // K.  Measured on the MobileNetV2 projections with K = 576 / 960: 0.146 -> 0.140, 0.069 -> 0.060, 0.125 -> 0.096 ms.)
-      const int g2_min_k = getenv("QNNP_CUDA_GEMM2SM_MIN_K") != nullptr ? atoi(getenv("QNNP_CUDA_GEMM2SM_MIN_K")) : 512;
+      // K.  Measured on the MobileNetV2 projections with K = 960: 0.064 -> 0.058, 0.113 -> 0.095 ms; at K = 576 the single-CTA
+      // kernel is the faster one since it loads its activations as 32-byte slabs: 0.105 vs 0.139 ms.)
+      const int g2_min_k = getenv("QNNP_CUDA_GEMM2SM_MIN_K") != nullptr ? atoi(getenv("QNNP_CUDA_GEMM2SM_MIN_K")) : 768;
       if (op->d_w2 != nullptr && op->K >= g2_min_k && mode == q8::kModeGemm && (op->rq_mode == 5 || op->rq_mode == 6) && M >= 256 &&
           ((uintptr_t) in % 16) == 0 && (op->in_stride % 16) == 0 && ((uintptr_t) out % 16) == 0 && (op->out_stride % 16) == 0 &&
           g_lib.dbg_acc == nullptr && !env_set("QNNP_CUDA_NO_GEMM2SM")) {
